@@ -1,0 +1,67 @@
+# stereomatching-b200 -- build of the C-ABI library, the host drivers and the oracle.
+#
+# Keeps the reference Makefile's contract (reference Makefile:4-31): the same binary
+# names, `build=debug|timing|release` output directories, -DDEBUG in debug (PPM dumps go
+# to par/ and pargh/ for test/diff.sh) and -DNO_WRITES in timing.  What is new: the CUDA
+# side is one shared library built for sm_100a, and the drivers are plain C.
+#
+#   make lib                      stereomatching_b200/libstereo_b200.so
+#   make [build=debug]            debug/stereopar debug/stereopar-ghost
+#   make build=timing             timing/...
+#   make oracle                   oracle/liboracle.so (+ oracle/_ref when /root/reference exists)
+
+build   := debug
+CC      := gcc
+NVCC    := nvcc
+SM_ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 $(SM_ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall
+CFLAGS  := -Wall -Wextra -std=gnu11 -Wno-unused-parameter -Iinclude
+
+ifeq ($(build),debug)
+    outdir := debug
+    CFLAGS += -g -DDEBUG
+else ifeq ($(build),timing)
+    outdir := timing
+    CFLAGS += -O3 -DNO_WRITES
+else ifeq ($(build),release)
+    outdir := release
+    CFLAGS += -O3
+else
+    $(error error: invalid value for build)
+endif
+
+CSRC   := stereomatching_b200/csrc
+LIB    := stereomatching_b200/libstereo_b200.so
+KOBJS  := $(patsubst %,$(CSRC)/build/%.o,stereo_b200 k_edges k_pack k_direct k_bitslice k_step3)
+
+all: lib $(outdir)/stereopar $(outdir)/stereopar-ghost
+
+lib: $(LIB)
+
+$(CSRC)/build/%.o: $(CSRC)/%.cu $(CSRC)/sm_common.cuh include/stereo_b200.h
+	@mkdir -p $(CSRC)/build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(KOBJS)
+	$(NVCC) $(SM_ARCH) -shared $(KOBJS) -o $@
+
+$(outdir):
+	mkdir -p $(outdir)
+
+# Host drivers: plain C, the reference's main()/algorithm() flow over the C ABI.
+$(outdir)/stereopar: host/driver.c host/hostimage.c host/hostimage.h include/stereo_b200.h $(LIB) | $(outdir)
+	$(CC) $(CFLAGS) -DSM_VARIANT=0 host/driver.c host/hostimage.c -o $@ \
+	    -Lstereomatching_b200 -lstereo_b200 -Wl,-rpath,'$$ORIGIN/../stereomatching_b200' -lz -lm
+
+$(outdir)/stereopar-ghost: host/driver.c host/hostimage.c host/hostimage.h include/stereo_b200.h $(LIB) | $(outdir)
+	$(CC) $(CFLAGS) -DSM_VARIANT=1 host/driver.c host/hostimage.c -o $@ \
+	    -Lstereomatching_b200 -lstereo_b200 -Wl,-rpath,'$$ORIGIN/../stereomatching_b200' -lz -lm
+
+oracle:
+	$(MAKE) -C oracle liboracle.so
+	if [ -d /root/reference/src ]; then $(MAKE) -C oracle ref; fi
+
+clean:
+	-rm -rf debug timing release $(CSRC)/build $(LIB)
+
+.PHONY: all lib oracle clean

@@ -1,0 +1,96 @@
+// k_pack.cu -- u8 edge maps -> padded 1-bit planes LA / LB / RB (see sm_common.cuh).
+//
+// This is the "image upload and layout path" of the hot path: the two W*H byte maps
+// become three bit planes over the band plus its halo, with the border policy of the
+// variant (toroidal wrap, util.h:42-47, or zero ghost cells, ghost.h / stereo-ghost.c:
+// 93-97,286-287) baked into the padding, so the main kernels carry no border logic.
+// It stands in for fillup_matches' index arithmetic (stereo.cu:127-137) and for
+// ghost_alloc_gpu / ghost_add_gpu (ghost.h:61-98).
+//
+// One thread produces one 32-bit word of each plane (32 pixels).  Interior words of
+// 16-byte aligned rows take the fast path: two 128-bit loads per map and a multiply
+// that gathers the low bit of 4 bytes into a nibble.
+#include "sm_common.cuh"
+
+namespace smb {
+
+__device__ __forceinline__ uint32_t gather4(uint32_t v)
+{
+    // bytes b0..b3 in {0,1}  ->  bits 0..3
+    return ((v & 0x01010101u) * 0x01020408u) >> 24;
+}
+
+__device__ __forceinline__ uint32_t gather32(const uint4 &a, const uint4 &b)
+{
+    return gather4(a.x) | (gather4(a.y) << 4) | (gather4(a.z) << 8) | (gather4(a.w) << 12) |
+           (gather4(b.x) << 16) | (gather4(b.y) << 20) | (gather4(b.z) << 24) | (gather4(b.w) << 28);
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, int row0,
+       PackedGeom g, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB, uint32_t *__restrict__ RB)
+{
+    int wd = blockIdx.x * blockDim.x + threadIdx.x;
+    int pr = blockIdx.y;
+    if (wd >= g.WPR) return;
+    int y = row0 - g.half + pr;
+    bool rowvalid = true;
+    if (VARIANT == SM_WRAP) {
+        y %= FH;
+        if (y < 0) y += FH;
+    } else {
+        rowvalid = y >= 0 && y < FH;
+    }
+    uint32_t l = 0, r = 0, v = 0;
+    if (rowvalid) {
+        const uint8_t *p1 = e1 + (size_t)y * g.W;
+        const uint8_t *p2 = e2 + (size_t)y * g.W;
+        int x0 = wd * 32 - PADL;
+        bool fast = x0 >= 0 && x0 + 32 <= g.W && (g.W & 15) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(e1) | reinterpret_cast<uintptr_t>(e2)) & 15) == 0;
+        if (fast) {
+            const uint4 *q1 = reinterpret_cast<const uint4 *>(p1 + x0);
+            const uint4 *q2 = reinterpret_cast<const uint4 *>(p2 + x0);
+            uint4 a0 = __ldg(q1), a1 = __ldg(q1 + 1), b0 = __ldg(q2), b1 = __ldg(q2 + 1);
+            l = gather32(a0, a1);
+            r = gather32(b0, b1);
+            v = 0xFFFFFFFFu;
+        } else {
+            for (int b = 0; b < 32; b++) {
+                int x = x0 + b;
+                bool ok = true;
+                if (VARIANT == SM_WRAP) {
+                    x %= g.W;
+                    if (x < 0) x += g.W;
+                } else {
+                    ok = x >= 0 && x < g.W;
+                }
+                if (ok) {
+                    l |= (uint32_t)(p1[x] & 1) << b;
+                    r |= (uint32_t)(p2[x] & 1) << b;
+                    v |= 1u << b;
+                }
+            }
+        }
+    }
+    size_t o = (size_t)pr * g.WPR + wd;
+    LA[o] = l & v;
+    LB[o] = ~l & v;
+    RB[o] = r & v;
+}
+
+int launch_pack(const uint8_t *e1, const uint8_t *e2, int FH, int row0, int variant,
+                const PackedGeom &g, uint32_t *LA, uint32_t *LB, uint32_t *RB, cudaStream_t s)
+{
+    dim3 block(64);
+    dim3 grid((g.WPR + block.x - 1) / block.x, g.ER);
+    if (variant == SM_WRAP)
+        k_pack<SM_WRAP><<<grid, block, 0, s>>>(e1, e2, FH, row0, g, LA, LB, RB);
+    else
+        k_pack<SM_GHOST><<<grid, block, 0, s>>>(e1, e2, FH, row0, g, LA, LB, RB);
+    SM_CUDA(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace smb

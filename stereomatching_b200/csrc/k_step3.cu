@@ -1,0 +1,126 @@
+// k_step3.cu -- step 3 of the reference and small utilities.
+//
+//   fill_web_holes_step  stereo.cu:235-245   (32 launches from fill_web_holes :247-259)
+//   array_min/max_gpu    util.cu:15-45       (two launches + malloc/H2D/D2H each)
+//   draw_contour_map     stereo.cu:261-274
+// Here: one hole-filling kernel per iteration, ONE fused min+max reduction (warp
+// shuffles, one atomic pair per block) and the contour kernel.
+#include <limits.h>
+
+#include "sm_common.cuh"
+
+namespace smb {
+
+// web is never 0 after step 2 (every pixel gets some i+1), so the branch body never
+// runs on real data.  The reference reads the four neighbours without
+// bounds checks (stereo.cu:240-243); out-of-frame neighbours are taken as 0 here.
+__global__ void __launch_bounds__(256)
+k_fill_holes(const int32_t *__restrict__ src, int32_t *__restrict__ dst, int W, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    size_t p = (size_t)y * W + x;
+    if (src[p] == 0) {
+        int32_t r = x + 1 < W ? src[p + 1] : 0, l = x > 0 ? src[p - 1] : 0;
+        int32_t u = y + 1 < H ? src[p + W] : 0, d = y > 0 ? src[p - W] : 0;
+        dst[p] = (r + u + l + d) / 4;
+    }
+    // cells that are not holes keep what the destination buffer already holds, exactly
+    // like the reference's ping-pong between web and tmp (stereo.cu:247-259)
+}
+
+int launch_fill_web_holes_step(const int32_t *src, int32_t *dst, int W, int H, cudaStream_t s)
+{
+    dim3 block(64, 4);
+    dim3 grid((W + block.x - 1) / block.x, (H + block.y - 1) / block.y);
+    k_fill_holes<<<grid, block, 0, s>>>(src, dst, W, H);
+    SM_CUDA(cudaGetLastError());
+    return 1;
+}
+
+__global__ void k_minmax_init(int32_t *mm)
+{
+    mm[0] = INT_MAX;
+    mm[1] = INT_MIN;
+}
+
+__global__ void __launch_bounds__(256) k_minmax(const int32_t *__restrict__ a, size_t n, int32_t *mm)
+{
+    int32_t mn = INT_MAX, mx = INT_MIN;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        int32_t v = a[i];
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    __shared__ int32_t smn[8], smx[8];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        smn[w] = mn;
+        smx[w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) {
+            mn = min(mn, smn[k]);
+            mx = max(mx, smx[k]);
+        }
+        atomicMin(mm, mn);
+        atomicMax(mm + 1, mx);
+    }
+}
+
+int launch_minmax(const int32_t *a, size_t n, int32_t *d_minmax, cudaStream_t s)
+{
+    k_minmax_init<<<1, 1, 0, s>>>(d_minmax);
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    k_minmax<<<blocks, 256, 0, s>>>(a, n, d_minmax);
+    SM_CUDA(cudaGetLastError());
+    return 2;
+}
+
+// out = ((web - min) % interval) == 0   (stereo.cu:261-274)
+__global__ void __launch_bounds__(256)
+k_contour(const int32_t *__restrict__ web, size_t n, int32_t mn, int32_t interval,
+          uint8_t *__restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ((web[i] - mn) % interval) == 0;
+}
+
+int launch_contour(const int32_t *web, size_t n, int32_t mn, int32_t interval, uint8_t *out,
+                   cudaStream_t s)
+{
+    k_contour<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(web, n, mn, interval, out);
+    SM_CUDA(cudaGetLastError());
+    return 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_i32_to_u8(const int32_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n)
+{
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        int4 v = *reinterpret_cast<const int4 *>(src + i);
+        uchar4 o = make_uchar4((unsigned char)v.x, (unsigned char)v.y, (unsigned char)v.z,
+                               (unsigned char)v.w);
+        *reinterpret_cast<uchar4 *>(dst + i) = o;
+    } else {
+        for (; i < n; i++) dst[i] = (uint8_t)src[i];
+    }
+}
+
+int launch_i32_to_u8(const int32_t *src, uint8_t *dst, size_t n, cudaStream_t s)
+{
+    size_t q = (n + 3) / 4;
+    k_i32_to_u8<<<(unsigned)((q + 255) / 256), 256, 0, s>>>(src, dst, n);
+    SM_CUDA(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace smb

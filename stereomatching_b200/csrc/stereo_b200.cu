@@ -1,0 +1,654 @@
+// stereo_b200.cu -- the C ABI of include/stereo_b200.h: context, transfers, orchestration.
+//
+// Stands in for the host side of the reference's CUDA programs: main()'s
+// MAKE_GPU_COPY uploads (stereo.cu:402-403), algorithm()'s allocations, launch
+// sequence and frees (stereo.cu:296-347), write_gpu_image's D2H (image.cu:15-23) and
+// the min/max helpers (util.cu:34-42).  No kernel lives here (k_*.cu).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+
+#include "sm_common.cuh"
+
+namespace smb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+struct sm_ctx {
+    int device = 0;
+    int W = 0, FH = 0;         // frame geometry
+    int row0 = 0, row1 = 0;    // output rows owned by this context
+    int D = 0, sw = 0, half = 0, variant = 0;
+    int kernel = SM_KERNEL_AUTO;
+    int num_sms = 148;
+    PackedGeom g{};
+
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int last_launches = 0;
+
+    // frame-sized device arrays (a band context touches only the rows it needs)
+    uint8_t *img_u8[2] = {nullptr, nullptr};
+    double *img_f64[2] = {nullptr, nullptr};
+    int img_kind = 0;  // 0 none, 1 u8, 2 f64
+    uint8_t *edges[2] = {nullptr, nullptr};
+    bool have_edges = false;
+    int32_t *best = nullptr, *web = nullptr;
+    bool have_web = false;
+    int32_t *web2 = nullptr, *tmp = nullptr;  // step 3 ping-pong
+    bool have_web2 = false;
+    uint8_t *out = nullptr;
+    bool have_out = false;
+    int32_t *minmax = nullptr;
+    // band-sized packed planes
+    uint32_t *LA = nullptr, *LB = nullptr, *RB = nullptr;
+    // scratch for on-demand debug planes / u8 web
+    uint8_t *scratch_u8 = nullptr;
+    int32_t *scratch_i32 = nullptr;
+
+    sm_ctx *shadow = nullptr;  // second pipeline slot of sm_run_batch
+
+    size_t npix() const { return (size_t)W * FH; }
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define SM_ENTER(ctx)                                                   \
+    if (!(ctx)) {                                                       \
+        set_error("%s: NULL context", __func__);                        \
+        return SM_ERR_ARG;                                              \
+    }                                                                   \
+    DeviceGuard guard__((ctx)->device);                                 \
+    if (!guard__.ok) {                                                  \
+        set_error("%s: cudaSetDevice(%d) failed", __func__, (ctx)->device); \
+        return SM_ERR_CUDA;                                             \
+    }
+
+template <typename T>
+int dev_alloc(T **p, size_t count)
+{
+    if (*p) return SM_OK;
+    SM_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+    return SM_OK;
+}
+
+// Frame rows [lo, hi) as up to a few contiguous [start, start+count) runs inside the
+// frame: wrapped mod FH for WRAP (util.h:42-47), clipped for GHOST.
+struct RowRuns {
+    int n = 0;
+    int start[4], count[4];
+};
+
+RowRuns row_runs(int lo, int hi, int FH, bool wrap)
+{
+    RowRuns r;
+    if (hi - lo >= FH) {
+        r.n = 1;
+        r.start[0] = 0;
+        r.count[0] = FH;
+        return r;
+    }
+    if (!wrap) {
+        lo = lo < 0 ? 0 : lo;
+        hi = hi > FH ? FH : hi;
+        if (hi > lo) {
+            r.n = 1;
+            r.start[0] = lo;
+            r.count[0] = hi - lo;
+        }
+        return r;
+    }
+    int a = ((lo % FH) + FH) % FH, len = hi - lo;
+    while (len > 0 && r.n < 4) {
+        int c = len < FH - a ? len : FH - a;
+        r.start[r.n] = a;
+        r.count[r.n] = c;
+        r.n++;
+        len -= c;
+        a = 0;
+    }
+    return r;
+}
+
+template <typename T>
+int copy_rows_h2d(sm_ctx *c, T *dst, const T *src, int lo, int hi)
+{
+    RowRuns rr = row_runs(lo, hi, c->FH, c->variant == SM_WRAP);
+    for (int k = 0; k < rr.n; k++) {
+        size_t off = (size_t)rr.start[k] * c->W;
+        SM_CUDA(cudaMemcpyAsync(dst + off, src + off, (size_t)rr.count[k] * c->W * sizeof(T),
+                                cudaMemcpyHostToDevice, c->stream));
+    }
+    return SM_OK;
+}
+
+template <typename T>
+int copy_band_d2h(sm_ctx *c, T *host, const T *dev)
+{
+    size_t off = (size_t)c->row0 * c->W;
+    SM_CUDA(cudaMemcpyAsync(host + off, dev + off, (size_t)(c->row1 - c->row0) * c->W * sizeof(T),
+                            cudaMemcpyDeviceToHost, c->stream));
+    return SM_OK;
+}
+
+HotArgs hot_args(sm_ctx *c, int32_t *best, int32_t *web)
+{
+    HotArgs a;
+    a.g = c->g;
+    a.LA = c->LA;
+    a.LB = c->LB;
+    a.RB = c->RB;
+    a.best = best;
+    a.web = web;
+    a.row0 = c->row0;
+    return a;
+}
+
+int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int32_t *web)
+{
+    int launches = 0, rc;
+    SM_CUDA(cudaEventRecord(c->ev0, c->stream));
+    rc = launch_pack(e1, e2, c->FH, c->row0, c->variant, c->g, c->LA, c->LB, c->RB, c->stream);
+    if (rc < 0) return rc;
+    launches += rc;
+    HotArgs a = hot_args(c, best, web);
+    int k = c->kernel;
+    if (k == SM_KERNEL_AUTO) k = bitslice_supports(c->half, c->D) ? SM_KERNEL_BITSLICE : SM_KERNEL_DIRECT;
+    if (k == SM_KERNEL_BITSLICE) {
+        if (!bitslice_supports(c->half, c->D)) {
+            set_error("bit-sliced kernel does not cover square_width %d / num_shifts %d", c->sw, c->D);
+            return SM_ERR_ARG;
+        }
+        rc = launch_bitslice(a, c->num_sms, c->stream);
+    } else {
+        rc = launch_direct(a, c->stream);
+    }
+    if (rc < 0) return rc;
+    launches += rc;
+    SM_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    c->last_launches = launches;
+    return SM_OK;
+}
+
+}  // namespace
+
+// ---- library-level ---------------------------------------------------------------
+
+extern "C" const char *sm_last_error(void) { return g_err; }
+
+extern "C" int sm_version(void) { return (1 << 16) | 0; }
+
+extern "C" int sm_device_count(void)
+{
+    int n = 0;
+    SM_CUDA(cudaGetDeviceCount(&n));
+    return n;
+}
+
+extern "C" int sm_host_alloc(void **ptr, size_t bytes)
+{
+    SM_REQUIRE(ptr, "sm_host_alloc: NULL ptr");
+    SM_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return SM_OK;
+}
+
+extern "C" int sm_host_free(void *ptr)
+{
+    if (ptr) SM_CUDA(cudaFreeHost(ptr));
+    return SM_OK;
+}
+
+extern "C" int sm_band_rows(int height, int n_bands, int band, int *row0, int *row1)
+{
+    SM_REQUIRE(height > 0 && n_bands > 0 && band >= 0 && band < n_bands && row0 && row1,
+               "sm_band_rows: bad arguments");
+    // as even as possible: the first (height % n_bands) bands get one extra row
+    int q = height / n_bands, r = height % n_bands;
+    *row0 = band * q + (band < r ? band : r);
+    *row1 = *row0 + q + (band < r ? 1 : 0);
+    return SM_OK;
+}
+
+// ---- context -----------------------------------------------------------------------
+
+extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_height, int row0,
+                              int row1, int num_shifts, int square_width, int variant)
+{
+    SM_REQUIRE(out, "sm_create: NULL ctx pointer");
+    *out = nullptr;
+    SM_REQUIRE(width > 0 && frame_height > 0, "sm_create: width/height must be positive");
+    SM_REQUIRE((size_t)width * frame_height < ((size_t)1 << 31), "sm_create: frame too large");
+    SM_REQUIRE(num_shifts >= 1 && num_shifts <= 512, "sm_create: num_shifts must be in [1, 512]");
+    SM_REQUIRE(square_width >= 1 && square_width <= 63, "sm_create: square_width must be in [1, 63]");
+    // same check as the reference driver (stereo.cu:395-398)
+    SM_REQUIRE(square_width <= width && square_width <= frame_height,
+               "sm_create: square width must not be higher than image width/height");
+    SM_REQUIRE(variant == SM_WRAP || variant == SM_GHOST, "sm_create: unknown variant");
+    SM_REQUIRE(row0 >= 0 && row1 > row0 && row1 <= frame_height, "sm_create: bad row band");
+    int ndev = 0;
+    SM_CUDA(cudaGetDeviceCount(&ndev));
+    SM_REQUIRE(device >= 0 && device < ndev, "sm_create: device %d of %d", device, ndev);
+
+    sm_ctx *c = new (std::nothrow) sm_ctx;
+    if (!c) {
+        set_error("sm_create: out of memory");
+        return SM_ERR_NOMEM;
+    }
+    c->device = device;
+    DeviceGuard guard(device);
+    c->W = width;
+    c->FH = frame_height;
+    c->row0 = row0;
+    c->row1 = row1;
+    c->D = num_shifts;
+    c->sw = square_width;
+    c->half = square_width / 2;
+    c->variant = variant;
+    c->g.W = width;
+    c->g.BH = row1 - row0;
+    c->g.half = c->half;
+    c->g.ER = c->g.BH + 2 * c->half;
+    c->g.D = num_shifts;
+    c->g.WPR = packed_words_per_row(width, c->half, num_shifts);
+
+    int rc = SM_OK;
+    auto fail = [&](int code) {
+        sm_destroy(c);
+        return code;
+    };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+        set_error("sm_create: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(SM_ERR_CUDA);
+    }
+    c->own_stream = true;
+    size_t n = c->npix(), pw = (size_t)c->g.ER * c->g.WPR;
+    if ((rc = dev_alloc(&c->edges[0], n)) || (rc = dev_alloc(&c->edges[1], n)) ||
+        (rc = dev_alloc(&c->best, n)) || (rc = dev_alloc(&c->web, n)) ||
+        (rc = dev_alloc(&c->LA, pw)) || (rc = dev_alloc(&c->LB, pw)) || (rc = dev_alloc(&c->RB, pw)) ||
+        (rc = dev_alloc(&c->minmax, 2)))
+        return fail(rc);
+    *out = c;
+    return SM_OK;
+}
+
+extern "C" int sm_create(sm_ctx **ctx, int device, int width, int height, int num_shifts,
+                         int square_width, int variant)
+{
+    return sm_create_band(ctx, device, width, height, 0, height, num_shifts, square_width, variant);
+}
+
+extern "C" int sm_destroy(sm_ctx *c)
+{
+    if (!c) return SM_OK;
+    DeviceGuard guard(c->device);
+    if (c->shadow) sm_destroy(c->shadow);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->img_u8[0], c->img_u8[1], c->img_f64[0], c->img_f64[1], c->edges[0], c->edges[1],
+                    c->best,      c->web,       c->web2,       c->tmp,        c->out,      c->minmax,
+                    c->LA,        c->LB,        c->RB,         c->scratch_u8, c->scratch_i32};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SM_OK;
+}
+
+extern "C" int sm_set_stream(sm_ctx *c, void *cuda_stream)
+{
+    SM_ENTER(c);
+    if (c->own_stream && c->stream) {
+        SM_CUDA(cudaStreamSynchronize(c->stream));
+        SM_CUDA(cudaStreamDestroy(c->stream));
+    }
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    c->timed = false;
+    return SM_OK;
+}
+
+extern "C" int sm_set_kernel(sm_ctx *c, int kernel)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(kernel >= SM_KERNEL_AUTO && kernel <= SM_KERNEL_BITSLICE, "sm_set_kernel: unknown kernel");
+    c->kernel = kernel;
+    return SM_OK;
+}
+
+extern "C" int sm_synchronize(sm_ctx *c)
+{
+    SM_ENTER(c);
+    SM_CUDA(cudaStreamSynchronize(c->stream));
+    return SM_OK;
+}
+
+// ---- step 0: upload ------------------------------------------------------------------
+
+// rows of the brightness images this context reads: its output rows, the window halo,
+// and one more row for the 3x3 edge stencil
+static void image_rows(const sm_ctx *c, int *lo, int *hi)
+{
+    *lo = c->row0 - c->half - 1;
+    *hi = c->row1 + c->half + 1;
+}
+
+extern "C" int sm_upload_u8(sm_ctx *c, const uint8_t *first, const uint8_t *second)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(first && second, "sm_upload_u8: NULL image");
+    int rc, lo, hi;
+    if ((rc = dev_alloc(&c->img_u8[0], c->npix())) || (rc = dev_alloc(&c->img_u8[1], c->npix()))) return rc;
+    image_rows(c, &lo, &hi);
+    if ((rc = copy_rows_h2d(c, c->img_u8[0], first, lo, hi)) ||
+        (rc = copy_rows_h2d(c, c->img_u8[1], second, lo, hi)))
+        return rc;
+    c->img_kind = 1;
+    return SM_OK;
+}
+
+extern "C" int sm_upload_f64(sm_ctx *c, const double *first, const double *second)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(first && second, "sm_upload_f64: NULL image");
+    int rc, lo, hi;
+    if ((rc = dev_alloc(&c->img_f64[0], c->npix())) || (rc = dev_alloc(&c->img_f64[1], c->npix()))) return rc;
+    image_rows(c, &lo, &hi);
+    if ((rc = copy_rows_h2d(c, c->img_f64[0], first, lo, hi)) ||
+        (rc = copy_rows_h2d(c, c->img_f64[1], second, lo, hi)))
+        return rc;
+    c->img_kind = 2;
+    return SM_OK;
+}
+
+// ---- step 1: edges -------------------------------------------------------------------
+
+extern "C" int sm_edges(sm_ctx *c, double threshold)
+{
+    SM_ENTER(c);
+    if (c->img_kind == 0) {
+        set_error("sm_edges: no image uploaded");
+        return SM_ERR_STATE;
+    }
+    // same range check as the reference driver (stereo.cu:391-394)
+    SM_REQUIRE(threshold >= 0.0 && threshold <= 1.0, "sm_edges: threshold must be between 0 and 1");
+    int ystart = c->row0 - c->half, nrows = c->g.ER;
+    if (nrows >= c->FH) {
+        ystart = 0;
+        nrows = c->FH;
+    }
+    for (int k = 0; k < 2; k++) {
+        int rc = c->img_kind == 1
+                     ? launch_edges<uint8_t>(c->img_u8[k], c->W, c->FH, ystart, nrows, c->variant,
+                                             threshold, c->edges[k], c->stream)
+                     : launch_edges<double>(c->img_f64[k], c->W, c->FH, ystart, nrows, c->variant,
+                                            threshold, c->edges[k], c->stream);
+        if (rc < 0) return rc;
+    }
+    c->have_edges = true;
+    return SM_OK;
+}
+
+extern "C" int sm_set_edges(sm_ctx *c, const uint8_t *first_edges, const uint8_t *second_edges)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(first_edges && second_edges, "sm_set_edges: NULL edge map");
+    int rc;
+    if ((rc = copy_rows_h2d(c, c->edges[0], first_edges, c->row0 - c->half, c->row1 + c->half)) ||
+        (rc = copy_rows_h2d(c, c->edges[1], second_edges, c->row0 - c->half, c->row1 + c->half)))
+        return rc;
+    c->have_edges = true;
+    return SM_OK;
+}
+
+// ---- step 2: the hot path --------------------------------------------------------------
+
+extern "C" int sm_match_wta(sm_ctx *c)
+{
+    SM_ENTER(c);
+    if (!c->have_edges) {
+        set_error("sm_match_wta: no edges (call sm_edges or sm_set_edges first)");
+        return SM_ERR_STATE;
+    }
+    int rc = run_hot(c, c->edges[0], c->edges[1], c->best, c->web);
+    if (rc) return rc;
+    c->have_web = true;
+    c->have_web2 = c->have_out = false;
+    return SM_OK;
+}
+
+extern "C" int sm_match_wta_dev(sm_ctx *c, const uint8_t *d_first_edges, const uint8_t *d_second_edges,
+                                int32_t *d_best, int32_t *d_web)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(d_first_edges && d_second_edges && d_best && d_web, "sm_match_wta_dev: NULL pointer");
+    return run_hot(c, d_first_edges, d_second_edges, d_best, d_web);
+}
+
+extern "C" int sm_elapsed_ms(sm_ctx *c, float *ms)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(ms, "sm_elapsed_ms: NULL");
+    if (!c->timed) {
+        set_error("sm_elapsed_ms: no hot-path call has been made on this context");
+        return SM_ERR_STATE;
+    }
+    SM_CUDA(cudaEventSynchronize(c->ev1));
+    SM_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return SM_OK;
+}
+
+extern "C" int sm_last_launches(sm_ctx *c) { return c ? c->last_launches : SM_ERR_ARG; }
+
+// ---- step 3 ----------------------------------------------------------------------------
+
+extern "C" int sm_fill_web_holes(sm_ctx *c, int times)
+{
+    SM_ENTER(c);
+    if (!c->have_web) {
+        set_error("sm_fill_web_holes: no web (call sm_match_wta first)");
+        return SM_ERR_STATE;
+    }
+    SM_REQUIRE(times >= 0, "sm_fill_web_holes: times must be >= 0");
+    SM_REQUIRE(c->row0 == 0 && c->row1 == c->FH, "sm_fill_web_holes: whole-frame contexts only");
+    int rc;
+    size_t n = c->npix();
+    if ((rc = dev_alloc(&c->web2, n)) || (rc = dev_alloc(&c->tmp, n))) return rc;
+    // web2 <- web, tmp <- web (stereo.cu:328), then ping-pong (stereo.cu:247-259)
+    SM_CUDA(cudaMemcpyAsync(c->web2, c->web, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    SM_CUDA(cudaMemcpyAsync(c->tmp, c->web, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    int32_t *a = c->web2, *b = c->tmp;
+    for (int t = 0; t < times; t++) {
+        if ((rc = launch_fill_web_holes_step(b, a, c->W, c->FH, c->stream)) < 0) return rc;
+        int32_t *s = a;
+        a = b;
+        b = s;
+    }
+    c->web2 = a;  // whichever buffer the reference would return as `web`
+    c->tmp = b;
+    c->have_web2 = true;
+    return SM_OK;
+}
+
+extern "C" int sm_draw_contour_map(sm_ctx *c, int lines, int32_t *web_min, int32_t *web_max)
+{
+    SM_ENTER(c);
+    if (!c->have_web) {
+        set_error("sm_draw_contour_map: no web (call sm_match_wta first)");
+        return SM_ERR_STATE;
+    }
+    SM_REQUIRE(c->row0 == 0 && c->row1 == c->FH, "sm_draw_contour_map: whole-frame contexts only");
+    const int32_t *web = c->have_web2 ? c->web2 : c->web;
+    int rc;
+    if ((rc = dev_alloc(&c->out, c->npix()))) return rc;
+    if ((rc = launch_minmax(web, c->npix(), c->minmax, c->stream)) < 0) return rc;
+    int32_t mm[2];
+    SM_CUDA(cudaMemcpyAsync(mm, c->minmax, sizeof mm, cudaMemcpyDeviceToHost, c->stream));
+    SM_CUDA(cudaStreamSynchronize(c->stream));
+    if (web_min) *web_min = mm[0];
+    if (web_max) *web_max = mm[1];
+    // interval = (max - min) / num_lines (stereo.cu:276-285 -> stereo.c:265-266)
+    if (lines == 0 || (mm[1] - mm[0]) / lines == 0) {
+        set_error("sm_draw_contour_map: (max %d - min %d) / lines %d is zero; the reference divides by "
+                  "zero here", mm[1], mm[0], lines);
+        return SM_ERR_DEGENERATE;
+    }
+    if ((rc = launch_contour(web, c->npix(), mm[0], (mm[1] - mm[0]) / lines, c->out, c->stream)) < 0)
+        return rc;
+    c->have_out = true;
+    return SM_OK;
+}
+
+// ---- download ----------------------------------------------------------------------------
+
+extern "C" int sm_download(sm_ctx *c, int which, int shift, void *host)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(host, "sm_download: NULL host pointer");
+    int rc = SM_OK;
+    switch (which) {
+    case SM_EDGES1:
+    case SM_EDGES2:
+        if (!c->have_edges) goto state;
+        rc = copy_band_d2h(c, (uint8_t *)host, c->edges[which - SM_EDGES1]);
+        break;
+    case SM_MATCH:
+    case SM_SCORE_ALL:
+    case SM_SCORE: {
+        if (!c->have_edges) goto state;
+        SM_REQUIRE(shift >= 0 && shift < c->D, "sm_download: shift %d out of [0, %d)", shift, c->D);
+        if ((rc = dev_alloc(&c->scratch_u8, c->npix())) || (rc = dev_alloc(&c->scratch_i32, c->npix())))
+            return rc;
+        rc = launch_pack(c->edges[0], c->edges[1], c->FH, c->row0, c->variant, c->g, c->LA, c->LB, c->RB,
+                         c->stream);
+        if (rc < 0) return rc;
+        HotArgs a = hot_args(c, nullptr, nullptr);
+        rc = launch_planes(a, shift, which == SM_MATCH ? c->scratch_u8 : nullptr,
+                           which == SM_SCORE_ALL ? c->scratch_i32 : nullptr,
+                           which == SM_SCORE ? c->scratch_i32 : nullptr, c->stream);
+        if (rc < 0) return rc;
+        rc = which == SM_MATCH ? copy_band_d2h(c, (uint8_t *)host, c->scratch_u8)
+                               : copy_band_d2h(c, (int32_t *)host, c->scratch_i32);
+        break;
+    }
+    case SM_BEST:
+        if (!c->have_web) goto state;
+        rc = copy_band_d2h(c, (int32_t *)host, c->best);
+        break;
+    case SM_WEB:
+        if (!c->have_web) goto state;
+        rc = copy_band_d2h(c, (int32_t *)host, c->web);
+        break;
+    case SM_WEB_FILLED:
+        if (!c->have_web2) goto state;
+        rc = copy_band_d2h(c, (int32_t *)host, c->web2);
+        break;
+    case SM_OUTPUT:
+        if (!c->have_out) goto state;
+        rc = copy_band_d2h(c, (uint8_t *)host, c->out);
+        break;
+    default:
+        set_error("sm_download: unknown plane %d", which);
+        return SM_ERR_ARG;
+    }
+    if (rc) return rc;
+    SM_CUDA(cudaStreamSynchronize(c->stream));
+    return SM_OK;
+state:
+    set_error("sm_download: plane %d has not been computed yet", which);
+    return SM_ERR_STATE;
+}
+
+static int queue_web_u8(sm_ctx *c, uint8_t *host)
+{
+    int rc;
+    if ((rc = dev_alloc(&c->scratch_u8, c->npix()))) return rc;
+    size_t off = (size_t)c->row0 * c->W, n = (size_t)(c->row1 - c->row0) * c->W;
+    if ((rc = launch_i32_to_u8(c->web + off, c->scratch_u8 + off, n, c->stream)) < 0) return rc;
+    return copy_band_d2h(c, host, c->scratch_u8);
+}
+
+extern "C" int sm_download_web_u8(sm_ctx *c, uint8_t *host)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(host, "sm_download_web_u8: NULL host pointer");
+    SM_REQUIRE(c->D <= 255, "sm_download_web_u8: num_shifts %d does not fit 8 bits", c->D);
+    if (!c->have_web) {
+        set_error("sm_download_web_u8: no web (call sm_match_wta first)");
+        return SM_ERR_STATE;
+    }
+    int rc = queue_web_u8(c, host);
+    if (rc) return rc;
+    SM_CUDA(cudaStreamSynchronize(c->stream));
+    return SM_OK;
+}
+
+// ---- whole pairs, batched ----------------------------------------------------------------
+
+extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const uint8_t *second,
+                            double threshold, void *web_out, int web_u8, int32_t *best_out)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(n_pairs >= 0 && first && second && web_out, "sm_run_batch: bad arguments");
+    SM_REQUIRE(c->row0 == 0 && c->row1 == c->FH, "sm_run_batch: whole-frame contexts only");
+    SM_REQUIRE(!web_u8 || c->D <= 255, "sm_run_batch: u8 web needs num_shifts <= 255");
+    SM_REQUIRE(threshold >= 0.0 && threshold <= 1.0, "sm_run_batch: threshold must be between 0 and 1");
+    if (!c->shadow) {
+        int rc = sm_create(&c->shadow, c->device, c->W, c->FH, c->D, c->sw, c->variant);
+        if (rc) return rc;
+    }
+    c->shadow->kernel = c->kernel;
+    sm_ctx *slot[2] = {c, c->shadow};
+    size_t n = c->npix();
+    for (int k = 0; k < n_pairs; k++) {
+        sm_ctx *s = slot[k & 1];
+        int rc;
+        // the slot's previous pair (k-2) is complete once its stream has drained up to
+        // here; stream order alone makes reuse of the slot's buffers safe.
+        if ((rc = sm_upload_u8(s, first + (size_t)k * n, second + (size_t)k * n))) return rc;
+        if ((rc = sm_edges(s, threshold))) return rc;
+        if ((rc = sm_match_wta(s))) return rc;
+        if (web_u8)
+            rc = queue_web_u8(s, (uint8_t *)web_out + (size_t)k * n);
+        else
+            rc = copy_band_d2h(s, (int32_t *)web_out + (size_t)k * n, s->web);
+        if (rc) return rc;
+        if (best_out && (rc = copy_band_d2h(s, best_out + (size_t)k * n, s->best))) return rc;
+    }
+    SM_CUDA(cudaStreamSynchronize(c->stream));
+    SM_CUDA(cudaStreamSynchronize(c->shadow->stream));
+    return SM_OK;
+}
