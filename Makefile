@@ -32,7 +32,7 @@ endif
 
 CSRC   := stereomatching_b200/csrc
 LIB    := stereomatching_b200/libstereo_b200.so
-KOBJS  := $(patsubst %,$(CSRC)/build/%.o,stereo_b200 k_edges k_pack k_direct k_bitslice k_step3)
+KOBJS  := $(patsubst %,$(CSRC)/build/%.o,stereo_b200 k_edges k_pack k_direct k_bitslice k_step3 k_peak)
 
 all: lib $(outdir)/stereopar $(outdir)/stereopar-ghost
 

@@ -157,6 +157,21 @@ int sm_elapsed_ms(sm_ctx *ctx, float *ms);
 /* Number of kernels the last sm_match_wta* call launched. */
 int sm_last_launches(sm_ctx *ctx);
 
+/* Per-kernel timing of many hot-path calls without synchronising in between: after
+ * sm_profile_begin(ctx, max_calls) every sm_match_wta* call records its own event
+ * triple (before pack, between pack and the main kernel, after) on the context's
+ * stream; sm_profile_read waits for the stream and returns the number of calls
+ * recorded and the summed device time of the pack kernel and of the main kernel.
+ * bench.py's roofline figure comes from here.  sm_profile_begin(ctx, 0) switches it
+ * off. */
+int sm_profile_begin(sm_ctx *ctx, int max_calls);
+int sm_profile_read(sm_ctx *ctx, int *n_calls, double *pack_ms_total, double *main_ms_total);
+
+/* INT32 issue-rate microbenchmark (the roofline denominator of this path, which
+ * MEASURED_PEAKS.json does not carry): mode 0 IADD3, 1 LOP3, 2 IADD3+IMAD, 3 LOP3+IMAD.
+ * Result in 1e9 thread-instructions per second. */
+int sm_measure_int_peak(int device, int mode, double *gops_per_s);
+
 /* ---- step 3 --------------------------------------------------- */
 
 /* Replaces the D2D copy + fill_web_holes() (stereo.cu:328-329 -> :247-259, kernel

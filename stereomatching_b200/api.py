@@ -28,6 +28,7 @@ SYMBOLS = [
     "sm_create", "sm_create_band", "sm_destroy", "sm_set_stream", "sm_set_kernel",
     "sm_synchronize", "sm_upload_f64", "sm_upload_u8", "sm_edges", "sm_set_edges",
     "sm_match_wta", "sm_match_wta_dev", "sm_elapsed_ms", "sm_last_launches",
+    "sm_profile_begin", "sm_profile_read", "sm_measure_int_peak",
     "sm_fill_web_holes", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
     "sm_run_batch", "sm_band_rows",
 ]
@@ -67,6 +68,9 @@ def lib() -> C.CDLL:
         L.sm_match_wta_dev.argtypes = [vp, vp, vp, vp, vp]
         L.sm_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.sm_last_launches.argtypes = [vp]
+        L.sm_profile_begin.argtypes = [vp, i]
+        L.sm_profile_read.argtypes = [vp, C.POINTER(i), C.POINTER(d), C.POINTER(d)]
+        L.sm_measure_int_peak.argtypes = [i, i, C.POINTER(d)]
         L.sm_fill_web_holes.argtypes = [vp, i]
         L.sm_draw_contour_map.argtypes = [vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.sm_download.argtypes = [vp, i, i, vp]
@@ -85,6 +89,13 @@ def _check(rc: int) -> int:
 
 def device_count() -> int:
     return _check(lib().sm_device_count())
+
+
+def measure_int_peak(device: int = 0, mode: int = 2) -> float:
+    """INT32 issue rate in 1e9 thread-instructions/s (0 IADD3, 1 LOP3, 2 IADD3+IMAD, 3 LOP3+IMAD)."""
+    g = C.c_double()
+    _check(lib().sm_measure_int_peak(device, mode, C.byref(g)))
+    return g.value
 
 
 def band_rows(height: int, n_bands: int, band: int):
@@ -200,6 +211,15 @@ class StereoContext:
 
     def last_launches(self) -> int:
         return _check(lib().sm_last_launches(self._c))
+
+    def profile_begin(self, max_calls: int):
+        _check(lib().sm_profile_begin(self._c, max_calls))
+
+    def profile_read(self):
+        """(calls recorded, pack kernel ms total, main kernel ms total) since profile_begin."""
+        n, p, m = C.c_int(), C.c_double(), C.c_double()
+        _check(lib().sm_profile_read(self._c, C.byref(n), C.byref(p), C.byref(m)))
+        return n.value, p.value, m.value
 
     def fill_web_holes(self, times=32):
         _check(lib().sm_fill_web_holes(self._c, times))

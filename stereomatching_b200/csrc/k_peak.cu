@@ -1,0 +1,89 @@
+// k_peak.cu -- INT32 issue-rate microbenchmark: the roofline denominator of the hot path.
+//
+// MEASURED_PEAKS.json carries HBM GB/s and bf16 TFLOP/s only; this path is bound by the
+// integer ALU issue rate, so bench.py measures that peak on the box with
+// this kernel: long chains of independent 3-input integer instructions, operands rotated
+// so that ptxas can neither fold nor strength-reduce them.
+//   mode 0: IADD3            (alu pipe)
+//   mode 1: LOP3             (alu pipe)
+//   mode 2: IADD3 + IMAD     (alu + fma pipes together -- the dual-issue ceiling)
+//   mode 3: LOP3 + IMAD
+// Result: thread-instructions per second (one instruction = one "integer op").
+#include "sm_common.cuh"
+
+namespace smb {
+
+constexpr int PEAK_REGS = 8;
+constexpr int PEAK_UNROLL = 16;  // rounds per loop iteration; one round = PEAK_REGS instructions
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[PEAK_REGS];
+#pragma unroll
+    for (int k = 0; k < PEAK_REGS; k++) a[k] = seed * (k + 1) + threadIdx.x * 2654435761u + blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < PEAK_UNROLL; u++) {
+#pragma unroll
+            for (int k = 0; k < PEAK_REGS; k++) {
+                uint32_t x = a[k], y = a[(k + 1) % PEAK_REGS], z = a[(k + 3) % PEAK_REGS];
+                bool second = (k & 1) != 0;
+                if (MODE == 0 || (MODE == 2 && !second)) {
+                    asm volatile("{ .reg .u32 t; add.u32 t, %1, %2; add.u32 %0, t, %3; }"
+                                 : "=r"(a[k]) : "r"(x), "r"(y), "r"(z));
+                } else if (MODE == 1 || (MODE == 3 && !second)) {
+                    asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(a[k]) : "r"(x), "r"(y), "r"(z));
+                } else {
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(a[k]) : "r"(y), "r"(z), "r"(x));
+                }
+            }
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < PEAK_REGS; k++) r ^= a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+extern "C" int sm_measure_int_peak(int device, int mode, double *gops_per_s)
+{
+    SM_REQUIRE(gops_per_s && mode >= 0 && mode <= 3, "sm_measure_int_peak: bad arguments");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    SM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SM_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2000;
+    uint32_t *out = nullptr;
+    SM_CUDA(cudaMalloc(&out, (size_t)blocks * threads * sizeof(uint32_t)));
+    cudaEvent_t e0, e1;
+    SM_CUDA(cudaEventCreate(&e0));
+    SM_CUDA(cudaEventCreate(&e1));
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {  // rep 0 is the warm-up
+        SM_CUDA(cudaEventRecord(e0));
+        switch (mode) {
+        case 0: k_int_peak<0><<<blocks, threads>>>(out, iters, 17u + rep); break;
+        case 1: k_int_peak<1><<<blocks, threads>>>(out, iters, 17u + rep); break;
+        case 2: k_int_peak<2><<<blocks, threads>>>(out, iters, 17u + rep); break;
+        default: k_int_peak<3><<<blocks, threads>>>(out, iters, 17u + rep); break;
+        }
+        SM_CUDA(cudaEventRecord(e1));
+        SM_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        SM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    double instr = (double)blocks * threads * iters * PEAK_UNROLL * PEAK_REGS;
+    *gops_per_s = instr / (best_ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (prev >= 0) cudaSetDevice(prev);
+    return SM_OK;
+}

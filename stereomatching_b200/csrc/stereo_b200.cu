@@ -40,6 +40,9 @@ struct sm_ctx {
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    // sm_profile_*: one event triple per hot-path call
+    cudaEvent_t *prof_ev = nullptr;
+    int prof_cap = 0, prof_n = 0;
     int last_launches = 0;
 
     // frame-sized device arrays (a band context touches only the rows it needs)
@@ -176,10 +179,13 @@ HotArgs hot_args(sm_ctx *c, int32_t *best, int32_t *web)
 int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int32_t *web)
 {
     int launches = 0, rc;
+    cudaEvent_t *pe = (c->prof_ev && c->prof_n < c->prof_cap) ? c->prof_ev + 3 * c->prof_n : nullptr;
     SM_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if (pe) SM_CUDA(cudaEventRecord(pe[0], c->stream));
     rc = launch_pack(e1, e2, c->FH, c->row0, c->variant, c->g, c->LA, c->LB, c->RB, c->stream);
     if (rc < 0) return rc;
     launches += rc;
+    if (pe) SM_CUDA(cudaEventRecord(pe[1], c->stream));
     HotArgs a = hot_args(c, best, web);
     int k = c->kernel;
     if (k == SM_KERNEL_AUTO) k = bitslice_supports(c->half, c->D) ? SM_KERNEL_BITSLICE : SM_KERNEL_DIRECT;
@@ -195,9 +201,22 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
     if (rc < 0) return rc;
     launches += rc;
     SM_CUDA(cudaEventRecord(c->ev1, c->stream));
+    if (pe) {
+        SM_CUDA(cudaEventRecord(pe[2], c->stream));
+        c->prof_n++;
+    }
     c->timed = true;
     c->last_launches = launches;
     return SM_OK;
+}
+
+void profile_free(sm_ctx *c)
+{
+    for (int k = 0; k < 3 * c->prof_cap; k++)
+        if (c->prof_ev[k]) cudaEventDestroy(c->prof_ev[k]);
+    free(c->prof_ev);
+    c->prof_ev = nullptr;
+    c->prof_cap = c->prof_n = 0;
 }
 
 }  // namespace
@@ -321,6 +340,7 @@ extern "C" int sm_destroy(sm_ctx *c)
                     c->LA,        c->LB,        c->RB,         c->scratch_u8, c->scratch_i32};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    if (c->prof_ev) profile_free(c);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -472,6 +492,43 @@ extern "C" int sm_elapsed_ms(sm_ctx *c, float *ms)
 }
 
 extern "C" int sm_last_launches(sm_ctx *c) { return c ? c->last_launches : SM_ERR_ARG; }
+
+extern "C" int sm_profile_begin(sm_ctx *c, int max_calls)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(max_calls >= 0 && max_calls <= (1 << 20), "sm_profile_begin: bad max_calls");
+    SM_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->prof_ev) profile_free(c);
+    if (max_calls == 0) return SM_OK;
+    c->prof_ev = (cudaEvent_t *)calloc((size_t)3 * max_calls, sizeof(cudaEvent_t));
+    if (!c->prof_ev) {
+        set_error("sm_profile_begin: out of memory");
+        return SM_ERR_NOMEM;
+    }
+    c->prof_cap = max_calls;
+    for (int k = 0; k < 3 * max_calls; k++) SM_CUDA(cudaEventCreate(&c->prof_ev[k]));
+    return SM_OK;
+}
+
+extern "C" int sm_profile_read(sm_ctx *c, int *n_calls, double *pack_ms_total, double *main_ms_total)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(n_calls && pack_ms_total && main_ms_total, "sm_profile_read: NULL");
+    SM_CUDA(cudaStreamSynchronize(c->stream));
+    double p = 0, m = 0;
+    for (int k = 0; k < c->prof_n; k++) {
+        float a = 0, b = 0;
+        SM_CUDA(cudaEventElapsedTime(&a, c->prof_ev[3 * k], c->prof_ev[3 * k + 1]));
+        SM_CUDA(cudaEventElapsedTime(&b, c->prof_ev[3 * k + 1], c->prof_ev[3 * k + 2]));
+        p += a;
+        m += b;
+    }
+    *n_calls = c->prof_n;
+    *pack_ms_total = p;
+    *main_ms_total = m;
+    c->prof_n = 0;
+    return SM_OK;
+}
 
 // ---- step 3 ----------------------------------------------------------------------------
 

@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libstereo_b200.so), against
+the CPU oracle and the golden CRCs recorded from the unmodified reference.
+
+Bar: bit-exact (all integer work; the FP64 edge detector must reproduce the reference's
+0/1 decisions exactly, so it is compared array-for-array as well).
+"""
+import numpy as np
+import pytest
+
+import oracle
+import stereomatching_b200 as smb
+from util import FIXTURES, THRESHOLD, load_pair, vname
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [smb.KERNEL_DIRECT, smb.KERNEL_BITSLICE]
+KNAME = {smb.KERNEL_DIRECT: "direct", smb.KERNEL_BITSLICE: "bitslice"}
+
+
+def _ctx(w, h, D, sw, variant, kernel=smb.KERNEL_AUTO, rows=None):
+    return smb.StereoContext(w, h, D, sw, variant, rows=rows, kernel=kernel)
+
+
+def _run_edges(ctx, le, re):
+    best, web = ctx.match_wta_host(le, re)
+    return best, web
+
+
+# ---------------------------------------------------------------------------------
+# real fixtures, reference defaults: edges + best + web equal the reference's CRCs
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+@pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)
+@pytest.mark.parametrize("name", FIXTURES)
+def test_fixture_end_to_end(golden, name, variant, kernel):
+    if kernel == smb.KERNEL_DIRECT and name == "5-3840x2160":
+        pytest.skip("direct kernel at 4K is covered by the bit-sliced cross-check")
+    g = golden["fixture/%s/%s" % (name, vname(variant))]
+    a, b = load_pair(name)
+    h, w = a.shape
+    with _ctx(w, h, g["D"], g["sw"], variant, kernel) as c:
+        c.upload_u8(a, b)
+        c.edges(THRESHOLD)
+        e1, e2 = c.download(smb.EDGES1), c.download(smb.EDGES2)
+        assert oracle.crc32(e1) == g["edges1"] and oracle.crc32(e2) == g["edges2"]
+        c.match_wta()
+        best, web = c.download(smb.BEST), c.download(smb.WEB)
+        assert oracle.crc32(best) == g["best"]
+        assert oracle.crc32(web) == g["web"]
+        assert c.last_launches() >= 2 and c.elapsed_ms() > 0.0
+
+
+@pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)
+def test_small_fixture_arrays_equal_oracle(orc, variant):
+    a, b = load_pair("1-240x135")
+    h, w = a.shape
+    e1, e2 = orc.edges(a, THRESHOLD, variant), orc.edges(b, THRESHOLD, variant)
+    bo, wo = orc.match_wta(e1, e2, 30, 21, variant)
+    for kernel in KERNELS:
+        with _ctx(w, h, 30, 21, variant, kernel) as c:
+            c.upload_u8(a, b)
+            c.edges(THRESHOLD)
+            assert np.array_equal(c.download(smb.EDGES1), e1)
+            assert np.array_equal(c.download(smb.EDGES2), e2)
+            c.match_wta()
+            assert np.array_equal(c.download(smb.BEST), bo)
+            assert np.array_equal(c.download(smb.WEB), wo)
+
+
+def test_f64_upload_is_the_reference_layout(orc):
+    """sm_upload_f64 takes Image.data (double = u8/256.0, image.c:13) and must give the
+    same edges as the 8-bit upload, for several thresholds."""
+    a, b = load_pair("2-480x270")
+    h, w = a.shape
+    for variant in (smb.WRAP, smb.GHOST):
+        for thr in (0.0, 0.05, THRESHOLD, 0.6, 1.0):
+            with _ctx(w, h, 30, 21, variant) as c:
+                c.upload_f64(a / 256.0, b / 256.0)
+                c.edges(thr)
+                e1 = c.download(smb.EDGES1)
+                c.upload_u8(a, b)
+                c.edges(thr)
+                assert np.array_equal(c.download(smb.EDGES1), e1)
+                assert np.array_equal(e1, orc.edges(a, thr, variant))
+
+
+# ---------------------------------------------------------------------------------
+# synthetic config 2 (the bench workload) and the parameter sweep
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+@pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)
+def test_synth_c2(orc, golden, variant, kernel):
+    g = golden["synth/c2/%s" % vname(variant)]
+    left, right, disp = orc.synth_pair(1234, 1920, 1080, 64)
+    with _ctx(1920, 1080, 64, 9, variant, kernel) as c:
+        c.upload_u8(left, right)
+        c.edges(THRESHOLD)
+        c.match_wta()
+        e1, web, best = c.download(smb.EDGES1), c.download(smb.WEB), c.download(smb.BEST)
+    assert oracle.crc32(e1) == g["edges1"]
+    assert (oracle.crc32(best), oracle.crc32(web)) == (g["best"], g["web"])
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+def test_golden_sweep(orc, golden, kernel):
+    a, b = load_pair("1-240x135")
+    h, w = a.shape
+    n = 0
+    for k, g in sorted(golden.items()):
+        if not k.startswith("sweep/"):
+            continue
+        v = smb.GHOST if g["variant"] == "ghost" else smb.WRAP
+        if k.startswith("sweep/fix1/"):
+            left, right = a, b
+        else:
+            left, right, _ = orc.synth_pair(77, g["w"], g["h"], g["D"])
+        with _ctx(g["w"], g["h"], g["D"], g["sw"], v, kernel) as c:
+            c.upload_u8(left, right)
+            c.edges(THRESHOLD)
+            c.match_wta()
+            best, web = c.download(smb.BEST), c.download(smb.WEB)
+        assert (oracle.crc32(best), oracle.crc32(web)) == (g["best"], g["web"]), k
+        n += 1
+    assert n >= 80
+
+
+GEOMS = [  # (w, h, D, sw): odd widths, W not a multiple of 16/32, sw == min(w,h), D > W
+    (21, 21, 30, 21), (33, 17, 7, 3), (64, 64, 64, 9), (100, 37, 30, 21), (257, 33, 40, 5),
+    (130, 70, 130, 11), (48, 48, 512, 7), (19, 40, 64, 9), (512, 24, 33, 13), (96, 50, 1, 1),
+    (200, 45, 96, 15), (77, 31, 31, 17), (640, 40, 256, 11), (35, 35, 65, 2),
+]
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+@pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)
+def test_random_edge_maps_odd_geometries(orc, variant, kernel):
+    for gi, (w, h, D, sw) in enumerate(GEOMS):
+        rng = np.random.default_rng(1000 + gi)
+        dens = [0.05, 0.3, 0.5, 0.9][gi % 4]
+        le = (rng.random((h, w)) < dens).astype(np.uint8)
+        re = np.roll(le, rng.integers(0, max(1, min(D, w))), axis=1)
+        re ^= (rng.random((h, w)) < 0.02).astype(np.uint8)
+        bo, wo = orc.match_wta(le, re, D, sw, variant)
+        with _ctx(w, h, D, sw, variant, kernel) as c:
+            best, web = _run_edges(c, le, re)
+        assert np.array_equal(best, bo), (w, h, D, sw)
+        assert np.array_equal(web, wo), (w, h, D, sw)
+
+
+def test_degenerate_maps(orc):
+    for variant in (smb.WRAP, smb.GHOST):
+        for le, re in [(np.zeros((40, 50), np.uint8),) * 2, (np.ones((40, 50), np.uint8),) * 2,
+                       (np.ones((40, 50), np.uint8), np.zeros((40, 50), np.uint8))]:
+            bo, wo = orc.match_wta(le, re, 12, 5, variant)
+            for kernel in KERNELS:
+                with _ctx(50, 40, 12, 5, variant, kernel) as c:
+                    best, web = _run_edges(c, le, re)
+                assert np.array_equal(best, bo) and np.array_equal(web, wo)
+
+
+# ---------------------------------------------------------------------------------
+# debug planes (the reference's -DDEBUG dumps), step 3
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)
+def test_debug_planes(orc, variant):
+    a, b = load_pair("1-240x135")
+    h, w = a.shape
+    e1, e2 = orc.edges(a, THRESHOLD, variant), orc.edges(b, THRESHOLD, variant)
+    with _ctx(w, h, 30, 21, variant) as c:
+        c.set_edges(e1, e2)
+        for i in (0, 1, 13, 29):
+            m, sa, s = orc.shift_planes(e1, e2, 21, i, variant)
+            assert np.array_equal(c.download(smb.MATCH, i), m)
+            assert np.array_equal(c.download(smb.SCORE_ALL, i), sa)
+            assert np.array_equal(c.download(smb.SCORE, i), s)
+        with pytest.raises(smb.StereoError):
+            c.download(smb.MATCH, 30)
+
+
+def test_step3(orc):
+    a, b = load_pair("1-240x135")
+    h, w = a.shape
+    for variant in (smb.WRAP, smb.GHOST):
+        with _ctx(w, h, 30, 21, variant) as c:
+            c.upload_u8(a, b)
+            c.edges(THRESHOLD)
+            c.match_wta()
+            web = c.download(smb.WEB)
+            c.fill_web_holes(32)
+            filled = c.download(smb.WEB_FILLED)
+            assert np.array_equal(filled, orc.fill_web_holes(web, 32))
+            mn, mx = c.draw_contour_map(10)
+            assert (mn, mx) == (web.min(), web.max())
+            rc, out = orc.draw_contour_map(filled, 10)
+            assert rc == 0 and np.array_equal(c.download(smb.OUTPUT), out)
+            assert np.array_equal(c.download_web_u8(), web.astype(np.uint8))
+    # degenerate range: the reference divides by zero; the library reports it
+    z = np.zeros((32, 32), np.uint8)
+    with _ctx(32, 32, 8, 3, smb.WRAP) as c:
+        c.set_edges(z, z)
+        c.match_wta()
+        with pytest.raises(smb.StereoError) as ei:
+            c.draw_contour_map(10)
+        assert ei.value.code == smb.SM_ERR_DEGENERATE
+
+
+def test_state_errors():
+    with _ctx(64, 64, 30, 21, smb.WRAP) as c:
+        for call in (c.match_wta, c.edges, lambda: c.download(smb.WEB), lambda: c.fill_web_holes(1),
+                     c.elapsed_ms):
+            with pytest.raises(smb.StereoError):
+                call()
+        c.upload_u8(np.zeros((64, 64), np.uint8), np.zeros((64, 64), np.uint8))
+        with pytest.raises(smb.StereoError):
+            c.edges(1.5)  # threshold range, stereo.cu:391-394
+    with pytest.raises(smb.StereoError):
+        _ctx(64, 64, 30, 21, smb.WRAP, kernel=99)
+
+
+# ---------------------------------------------------------------------------------
+# row bands (multi-GPU shard contract) and batches of pairs
+# ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)
+@pytest.mark.parametrize("n_bands", [2, 3, 8])
+def test_row_bands_reassemble_the_frame(orc, variant, n_bands):
+    a, b = load_pair("2-480x270")
+    h, w = a.shape
+    e1, e2 = orc.edges(a, THRESHOLD, variant), orc.edges(b, THRESHOLD, variant)
+    bo, wo = orc.match_wta(e1, e2, 30, 21, variant)
+    best = np.full((h, w), -1, np.int32)
+    web = np.full((h, w), -1, np.int32)
+    ed = np.full((h, w), 255, np.uint8)
+    for band in range(n_bands):
+        rows = smb.band_rows(h, n_bands, band)
+        with _ctx(w, h, 30, 21, variant, rows=rows) as c:
+            c.upload_u8(a, b)  # whole-frame host arrays; only the band + halo rows are copied
+            c.edges(THRESHOLD)
+            c.match_wta()
+            c.download(smb.BEST, out=best)
+            c.download(smb.WEB, out=web)
+            c.download(smb.EDGES1, out=ed)
+    assert np.array_equal(ed, e1)
+    assert np.array_equal(best, bo) and np.array_equal(web, wo)
+
+
+def test_run_batch_equals_single_pairs(orc):
+    n, w, h, D, sw = 5, 320, 180, 64, 9
+    pairs = [orc.synth_pair(1234 + 2 * k, w, h, D) for k in range(n)]
+    first = np.stack([p[0] for p in pairs])
+    second = np.stack([p[1] for p in pairs])
+    for variant in (smb.WRAP, smb.GHOST):
+        with _ctx(w, h, D, sw, variant) as c:
+            web, best = c.run_batch(first, second, THRESHOLD, want_best=True)
+            web8 = c.run_batch(first, second, THRESHOLD, web_u8=True)
+        for k in range(n):
+            e1 = orc.edges(first[k], THRESHOLD, variant)
+            e2 = orc.edges(second[k], THRESHOLD, variant)
+            bo, wo = orc.match_wta(e1, e2, D, sw, variant)
+            assert np.array_equal(web[k], wo) and np.array_equal(best[k], bo)
+            assert np.array_equal(web8[k], wo.astype(np.uint8))
+
+
+def test_device_pointer_entry_with_torch(orc):
+    torch = pytest.importorskip("torch")
+    a, b = load_pair("1-240x135")
+    h, w = a.shape
+    e1, e2 = orc.edges(a, THRESHOLD, 0), orc.edges(b, THRESHOLD, 0)
+    bo, wo = orc.match_wta(e1, e2, 30, 21, 0)
+    d1 = torch.from_numpy(e1).cuda()
+    d2 = torch.from_numpy(e2).cuda()
+    best = torch.empty((h, w), dtype=torch.int32, device="cuda")
+    web = torch.empty((h, w), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    with _ctx(w, h, 30, 21, smb.WRAP) as c:
+        c.set_stream(torch.cuda.current_stream().cuda_stream)
+        c.match_wta_dev(d1.data_ptr(), d2.data_ptr(), best.data_ptr(), web.data_ptr())
+        torch.cuda.synchronize()
+        assert c.elapsed_ms() > 0
+    assert np.array_equal(best.cpu().numpy(), bo) and np.array_equal(web.cpu().numpy(), wo)
+
+
+# ---------------------------------------------------------------------------------
+# full-size properties (sizes the CPU oracle cannot finish in seconds)
+# ---------------------------------------------------------------------------------
+def test_config3_properties(orc):
+    """3840x2160, D=256, sw=11 (BASELINE config 3): known disparity in tile interiors,
+    bands == whole frame, bit-sliced == direct on a row sample."""
+    W, H, D, sw = 3840, 2160, 256, 11
+    left, right, disp = orc.synth_pair(1234, W, H, D)
+    with _ctx(W, H, D, sw, smb.GHOST) as c:
+        c.upload_u8(left, right)
+        c.edges(THRESHOLD)
+        c.match_wta()
+        web, best = c.download(smb.WEB), c.download(smb.BEST)
+        e1, e2 = c.download(smb.EDGES1), c.download(smb.EDGES2)
+    half, TW, TH = sw // 2, 4 * D, 120
+    ys, xs = np.mgrid[0:H, 0:W]
+    interior = ((xs % TW >= half) & (xs % TW < TW - D - half) & (ys % TH >= half + 1) &
+                (ys % TH < TH - half - 1) & (xs >= half + 1) & (xs < W - D - half - 1) &
+                (ys >= half + 1) & (ys < H - half - 1))
+    assert (web[interior] == disp[interior] + 1).mean() >= 0.9999
+    assert web.min() >= 1 and web.max() <= D and best.max() <= sw * sw and best.min() >= 0
+    # bands reassemble the frame
+    web_b = np.zeros_like(web)
+    for band in range(4):
+        with _ctx(W, H, D, sw, smb.GHOST, rows=smb.band_rows(H, 4, band)) as c:
+            c.upload_u8(left, right)
+            c.edges(THRESHOLD)
+            c.match_wta()
+            c.download(smb.WEB, out=web_b)
+    assert np.array_equal(web_b, web)
+    # oracle on a horizontal slab (rows 1000..1063 need rows 995..1068)
+    y0, y1 = 1000, 1064
+    sl = slice(y0 - half, y1 + half)
+    bo, wo = orc.match_wta(e1[sl], e2[sl], D, sw, smb.GHOST)
+    assert np.array_equal(wo[half:-half], web[y0:y1])
+    assert np.array_equal(bo[half:-half], best[y0:y1])
