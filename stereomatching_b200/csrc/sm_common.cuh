@@ -58,7 +58,9 @@ struct PackedGeom {
 
 inline int packed_words_per_row(int W, int half, int D)
 {
-    int bits = PADL + W + half + D + 96;  // slack: 64-bit window over-reads
+    // the bit-sliced kernel reads whole 64-column strips and 64-shift chunks; the slack
+    // covers its funnel-shift over-reads and the direct kernel's 64-bit windows
+    int bits = PADL + ((W + 63) & ~63) + ((D + 63) & ~63) + half + 160;
     int words = (bits + 31) / 32;
     return (words + 3) & ~3;
 }
