@@ -27,13 +27,13 @@ __device__ __forceinline__ uint32_t gather32(const uint4 &a, const uint4 &b)
 }
 
 template <int VARIANT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, int row0,
        PackedGeom g, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB, uint32_t *__restrict__ RB)
 {
-    int wd = blockIdx.x * blockDim.x + threadIdx.x;
-    int pr = blockIdx.y;
-    if (wd >= g.WPR) return;
+    const int wd = blockIdx.x * blockDim.x + threadIdx.x;  // lane <-> word, a warp covers 32 words
+    const int lane = threadIdx.x & 31;
+    const int pr = blockIdx.y;
     int y = row0 - g.half + pr;
     bool rowvalid = true;
     if (VARIANT == SM_WRAP) {
@@ -42,48 +42,56 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
     } else {
         rowvalid = y >= 0 && y < FH;
     }
+    const uint8_t *p1 = e1 + (size_t)(rowvalid ? y : 0) * g.W;
+    const uint8_t *p2 = e2 + (size_t)(rowvalid ? y : 0) * g.W;
+    const int x0 = wd * 32 - PADL;
+    const bool inrow = wd < g.WPR && rowvalid;
+    const bool fast = inrow && x0 >= 0 && x0 + 32 <= g.W && (g.W & 15) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(e1) | reinterpret_cast<uintptr_t>(e2)) & 15) == 0;
     uint32_t l = 0, r = 0, v = 0;
-    if (rowvalid) {
-        const uint8_t *p1 = e1 + (size_t)y * g.W;
-        const uint8_t *p2 = e2 + (size_t)y * g.W;
-        int x0 = wd * 32 - PADL;
-        bool fast = x0 >= 0 && x0 + 32 <= g.W && (g.W & 15) == 0 &&
-                    ((reinterpret_cast<uintptr_t>(e1) | reinterpret_cast<uintptr_t>(e2)) & 15) == 0;
-        if (fast) {
-            const uint4 *q1 = reinterpret_cast<const uint4 *>(p1 + x0);
-            const uint4 *q2 = reinterpret_cast<const uint4 *>(p2 + x0);
-            uint4 a0 = __ldg(q1), a1 = __ldg(q1 + 1), b0 = __ldg(q2), b1 = __ldg(q2 + 1);
-            l = gather32(a0, a1);
-            r = gather32(b0, b1);
-            v = 0xFFFFFFFFu;
+    if (fast) {
+        const uint4 *q1 = reinterpret_cast<const uint4 *>(p1 + x0);
+        const uint4 *q2 = reinterpret_cast<const uint4 *>(p2 + x0);
+        uint4 a0 = __ldg(q1), a1 = __ldg(q1 + 1), b0 = __ldg(q2), b1 = __ldg(q2 + 1);
+        l = gather32(a0, a1);
+        r = gather32(b0, b1);
+        v = 0xFFFFFFFFu;
+    }
+    // padding / ragged / unaligned words: the whole warp builds each one with ballots,
+    // lane b supplying pixel b of the word (wrapped or masked per the variant)
+    uint32_t slow = __ballot_sync(0xFFFFFFFFu, inrow && !fast);
+    while (slow) {
+        const int k = __ffs(slow) - 1;
+        slow &= slow - 1;
+        int x = (wd - lane + k) * 32 - PADL + lane;
+        bool ok = true;
+        if (VARIANT == SM_WRAP) {
+            x %= g.W;
+            if (x < 0) x += g.W;
         } else {
-            for (int b = 0; b < 32; b++) {
-                int x = x0 + b;
-                bool ok = true;
-                if (VARIANT == SM_WRAP) {
-                    x %= g.W;
-                    if (x < 0) x += g.W;
-                } else {
-                    ok = x >= 0 && x < g.W;
-                }
-                if (ok) {
-                    l |= (uint32_t)(p1[x] & 1) << b;
-                    r |= (uint32_t)(p2[x] & 1) << b;
-                    v |= 1u << b;
-                }
-            }
+            ok = x >= 0 && x < g.W;
+        }
+        const uint32_t lw = __ballot_sync(0xFFFFFFFFu, ok && (p1[ok ? x : 0] & 1));
+        const uint32_t rw = __ballot_sync(0xFFFFFFFFu, ok && (p2[ok ? x : 0] & 1));
+        const uint32_t vw = __ballot_sync(0xFFFFFFFFu, ok);
+        if (lane == k) {
+            l = lw;
+            r = rw;
+            v = vw;
         }
     }
-    size_t o = (size_t)pr * g.WPR + wd;
-    LA[o] = l & v;
-    LB[o] = ~l & v;
-    RB[o] = r & v;
+    if (wd < g.WPR) {
+        size_t o = (size_t)pr * g.WPR + wd;
+        LA[o] = l & v;
+        LB[o] = ~l & v;
+        RB[o] = r & v;
+    }
 }
 
 int launch_pack(const uint8_t *e1, const uint8_t *e2, int FH, int row0, int variant,
                 const PackedGeom &g, uint32_t *LA, uint32_t *LB, uint32_t *RB, cudaStream_t s)
 {
-    dim3 block(64);
+    dim3 block(128);
     dim3 grid((g.WPR + block.x - 1) / block.x, g.ER);
     if (variant == SM_WRAP)
         k_pack<SM_WRAP><<<grid, block, 0, s>>>(e1, e2, FH, row0, g, LA, LB, RB);
