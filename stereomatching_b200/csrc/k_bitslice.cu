@@ -33,6 +33,8 @@
 // rows so the row leaving the vertical window is still there.  More than 32*NW shifts are
 // processed as successive chunks over the same rows, merging (best, web) in place (a later
 // chunk holds higher shifts, so it wins ties).
+#include <stdlib.h>
+
 #include "sm_common.cuh"
 
 namespace smb {
@@ -110,6 +112,31 @@ __device__ __forceinline__ void planes_sub(uint32_t (&V)[PV], const uint32_t (&H
     }
 }
 
+// V += Hn - Ho in one ripple: d = Hn - Ho as KH planes plus a sign plane, then V += sext(d).
+// 2*KH + 2*PV - 1 ops instead of 2 * (2*PV - 1).
+template <int PV, int KH>
+__device__ __forceinline__ void planes_addsub(uint32_t (&V)[PV], const uint32_t (&Hn)[5], const uint32_t (&Ho)[5])
+{
+    uint32_t d[KH];
+    uint32_t b = ~Hn[0] & Ho[0];
+    d[0] = Hn[0] ^ Ho[0];
+#pragma unroll
+    for (int k = 1; k < KH; k++) {
+        d[k] = Hn[k] ^ Ho[k] ^ b;
+        b = (~Hn[k] & (Ho[k] | b)) | (Ho[k] & b);
+    }
+    const uint32_t sgn = b;  // lanes where Hn < Ho: d is negative, its upper planes are all ones
+    uint32_t c = V[0] & d[0];
+    V[0] ^= d[0];
+#pragma unroll
+    for (int k = 1; k < PV; k++) {
+        const uint32_t x = k < KH ? d[k] : sgn;
+        uint32_t sum = V[k] ^ x ^ c;
+        c = (V[k] & x) | (c & (V[k] ^ x));
+        V[k] = sum;
+    }
+}
+
 // What a walker needs from the packed planes of its row: 96 bits of RB starting at its
 // first pixel's first shift, and 64 bits each of LA / LB starting at its first pixel.
 struct WalkIn {
@@ -139,7 +166,44 @@ __device__ __forceinline__ WalkIn load_walk_in(const HotArgs &h, int pr, int rbi
     return o;
 }
 
-template <int HALF, int NW, int SEG>
+// One walk of pass A.  VALID_ALL: every pixel of the walk is inside the image (always so in
+// WRAP mode and away from the borders in GHOST mode), so the validity select drops out.
+template <int HALF, int NW, int SEG, bool VALID_ALL>
+__device__ __forceinline__ void walk(const WalkIn &in, uint4 *hq, uint32_t *h5, uint32_t *mq)
+{
+    using C = WS<HALF, NW, SEG>;
+    constexpr int N = C::N, KH = C::KH, STEPS = C::STEPS;
+    const uint32_t q[3] = {in.q0, in.q1, in.q2};
+    const uint32_t lw[2] = {in.a0, in.a1};
+    const uint32_t vw[2] = {in.a0 | in.b0, in.a1 | in.b1};
+    uint32_t P[5] = {0, 0, 0, 0, 0};
+    uint32_t m[STEPS];
+#pragma unroll
+    for (int t = 0; t < STEPS; t++) {
+        const int qi = t >> 5;
+        uint32_t mm = __funnelshift_r(q[qi], q[qi + 1 > 2 ? 2 : qi + 1], t & 31);
+        if (!(lw[t >> 5] & (1u << (t & 31)))) mm = ~mm;           // L(u) ? R : ~R
+        if (!VALID_ALL && !(vw[t >> 5] & (1u << (t & 31)))) mm = 0u;  // taps outside the image count nothing
+        m[t] = mm;
+        const uint32_t mout = t >= N ? m[t - N] : 0u;
+        // up/down counter: +1 where mm & ~mout, -1 where mout & ~mm
+        uint32_t c = (mm ^ mout) & (P[0] ^ mout);
+        P[0] ^= mm ^ mout;
+#pragma unroll
+        for (int k = 1; k < KH; k++) {
+            uint32_t cn = c & (P[k] ^ mout);
+            P[k] ^= c;
+            c = cn;
+        }
+        if (t >= 2 * HALF) {
+            hq[t - 2 * HALF] = make_uint4(P[0], P[1], P[2], P[3]);
+            if (KH > 4) h5[t - 2 * HALF] = P[4];
+        }
+        if (t >= HALF && t < HALF + SEG) mq[(t - HALF) * NW] = mm;  // centre word of pixel ws*SEG + t - HALF
+    }
+}
+
+template <int HALF, int NW, int SEG, bool MULTI>
 __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
 {
     using C = WS<HALF, NW, SEG>;
@@ -159,13 +223,20 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
     if (ja >= jb) return;
     const int ximg = x0 + lane;
     const bool store_ok = ximg < g.W;
-    const int nchunks = (g.D + 32 * NW - 1) / (32 * NW);
-    const int last_pr = jb + 2 * HALF;  // padded rows [ja, last_pr) feed this warp
+    const int nchunks = MULTI ? (g.D + 32 * NW - 1) / (32 * NW) : 1;
+    const int last_pr = jb + 2 * HALF;   // padded rows [ja, last_pr) feed this warp
+    const int first_out = ja + 2 * HALF; // the padded row that completes output row ja
 
     // walker role of this lane
     const int ws = lane / (NW * RB), wl = lane - ws * (NW * RB);
     const int wr = wl / NW, ww = wl - wr * NW;
     const int lbit = PADL + x0 + ws * SEG - HALF;  // first pixel of the walk, as a bit of LA / LB
+
+    auto load_h = [&](int slot, int w, uint32_t (&h)[5]) {
+        const uint4 qv = Hq[(slot * NW + w) * HROW + lane];
+        h[0] = qv.x, h[1] = qv.y, h[2] = qv.z, h[3] = qv.w;
+        h[4] = KH > 4 ? H5[(slot * NW + w) * HROW + lane] : 0u;
+    };
 
     for (int chunk = 0; chunk < nchunks; chunk++) {
         const int wg0 = chunk * NW;  // first 32-shift word of this chunk
@@ -178,20 +249,72 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
         }
         uint32_t V[NW][PV];
 #pragma unroll
-        for (int w = 0; w < NW; w++)
+        for (int w = 0; w < NW; w++) {
 #pragma unroll
             for (int p = 0; p < PV; p++) V[w][p] = 0;
+            // ring slot NR-1 stands for padded row ja-1: all zero, so that the first output row
+            // may subtract it like any other
+            Hq[((NR - 1) * NW + w) * HROW + lane] = make_uint4(0, 0, 0, 0);
+            if (KH > 4) H5[((NR - 1) * NW + w) * HROW + lane] = 0u;
+        }
 
         WalkIn in = {};
         if (ja + wr < last_pr) in = load_walk_in(a.h, ja + wr, rbit, lbit);
         int slot0 = 0, mslot0 = 0;  // ring slots of padded row p0
         size_t orow = (size_t)(a.h.row0 + ja) * g.W + ximg;  // output offset of the next row to be written
 
+        // one output row: V holds the window sums of row j; pick the winner and store it
+        auto emit = [&](int mslot_c) {
+            uint32_t M[NW], cand[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                M[w] = Mq[mslot_c * MROW + lane * NW + w];
+                cand[w] = valid[w];
+            }
+            int best = 0;
+            const int one = valid[0] ? 1 : g.W;  // always 1 (shift word 0 of a chunk has lanes); opaque to ptxas
+#pragma unroll
+            for (int p = PV - 1; p >= 0; p--) {
+                uint32_t t[NW], any = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    t[w] = cand[w] & V[w][p] & M[w];
+                    any |= t[w];
+                }
+                // predicated moves / multiply-add: ptxas places these on the FMA pipe, which is
+                // otherwise idle (the ALU pipe carries all the LOP3 work)
+                if (NW == 2) {
+                    asm("{ .reg .pred q; setp.ne.u32 q, %3, 0;\n\t"
+                        "@q mad.lo.u32 %0, %4, %6, 0;\n\t@q mad.lo.u32 %1, %5, %6, 0;\n\t@q mad.lo.s32 %2, %6, %7, %2; }"
+                        : "+r"(cand[0]), "+r"(cand[NW - 1]), "+r"(best)
+                        : "r"(any), "r"(t[0]), "r"(t[NW - 1]), "r"(one), "r"(1 << p));
+                } else {
+                    asm("{ .reg .pred q; setp.ne.u32 q, %2, 0;\n\t"
+                        "@q mad.lo.u32 %0, %3, %4, 0;\n\t@q mad.lo.s32 %1, %4, %5, %1; }"
+                        : "+r"(cand[0]), "+r"(best)
+                        : "r"(any), "r"(t[0]), "r"(one), "r"(1 << p));
+                }
+            }
+            int idx = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++)
+                if (cand[w]) idx = 32 * w + 31 - __clz(cand[w]);  // later words overwrite: highest lane
+            const int web = 32 * wg0 + idx + 1;
+            bool st = store_ok;
+            if (MULTI && chunk != 0 && st) st = best >= a.h.best[orow];  // a later chunk wins ties (higher shifts)
+            if (st) {
+                a.h.best[orow] = best;
+                a.h.web[orow] = web;
+            }
+            orow += g.W;
+        };
+
         for (int p0 = ja; p0 < last_pr; p0 += RB) {
             const int nrows = min(RB, last_pr - p0);
 
             // ---------------- pass A: 32 walkers ----------------
-            if (wr < nrows) {
+            {
+                const bool active = wr < nrows;
                 int slot = slot0 + wr;
                 slot = slot >= NR ? slot - NR : slot;
                 int mslot = mslot0 + wr;
@@ -199,34 +322,13 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
                 uint4 *hq = Hq + (slot * NW + ww) * HROW + ws * SEG;
                 uint32_t *h5 = H5 + (slot * NW + ww) * HROW + ws * SEG;
                 uint32_t *mq = Mq + mslot * MROW + (ws * SEG) * NW + ww;
-                const uint32_t q[3] = {in.q0, in.q1, in.q2};
-                const unsigned long long la = ((unsigned long long)in.a1 << 32) | in.a0;
-                const unsigned long long vl = la | (((unsigned long long)in.b1 << 32) | in.b0);
+                const unsigned long long vl =
+                    (((unsigned long long)(in.a1 | in.b1)) << 32) | (in.a0 | in.b0);
                 const bool all_valid = (~vl & ((1ull << STEPS) - 1ull)) == 0ull;
-                uint32_t P[5] = {0, 0, 0, 0, 0};
-                uint32_t m[STEPS];
-#pragma unroll
-                for (int t = 0; t < STEPS; t++) {
-                    const int qi = t >> 5;
-                    const uint32_t rwin = __funnelshift_r(q[qi], q[qi + 1 > 2 ? 2 : qi + 1], t & 31);
-                    uint32_t mm = ((la >> t) & 1ull) ? rwin : ~rwin;
-                    if (!all_valid) mm = ((vl >> t) & 1ull) ? mm : 0u;
-                    m[t] = mm;
-                    const uint32_t mout = t >= N ? m[t - N] : 0u;
-                    // up/down counter: +1 where mm & ~mout, -1 where mout & ~mm
-                    uint32_t c = (mm ^ mout) & (P[0] ^ mout);
-                    P[0] ^= mm ^ mout;
-#pragma unroll
-                    for (int k = 1; k < KH; k++) {
-                        uint32_t cn = c & (P[k] ^ mout);
-                        P[k] ^= c;
-                        c = cn;
-                    }
-                    if (t >= 2 * HALF) {
-                        hq[t - 2 * HALF] = make_uint4(P[0], P[1], P[2], P[3]);
-                        if (KH > 4) h5[t - 2 * HALF] = P[4];
-                    }
-                    if (t >= HALF && t < HALF + SEG) mq[(t - HALF) * NW] = mm;  // centre word of pixel ws*SEG + t - HALF
+                if (__all_sync(0xFFFFFFFFu, all_valid || !active)) {
+                    if (active) walk<HALF, NW, SEG, true>(in, hq, h5, mq);
+                } else {
+                    if (active) walk<HALF, NW, SEG, false>(in, hq, h5, mq);
                 }
             }
             __syncwarp();
@@ -235,66 +337,51 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
             if (p0 + RB + wr < last_pr) in = load_walk_in(a.h, p0 + RB + wr, rbit, lbit);
 
             // ---------------- pass B: 32 pixel columns ----------------
+            if (p0 >= first_out && nrows == RB) {
+                // steady state, branch-free: every row enters, one leaves, one output row
 #pragma unroll
-            for (int r = 0; r < RB; r++) {
-                if (r < nrows) {
+                for (int r = 0; r < RB; r++) {
+                    int slot_n = slot0 + r;
+                    slot_n = slot_n >= NR ? slot_n - NR : slot_n;
+                    int slot_o = slot_n - N;
+                    slot_o = slot_o < 0 ? slot_o + NR : slot_o;
+                    int mslot_c = mslot0 + r - HALF;
+                    mslot_c = mslot_c < 0 ? mslot_c + NRM : (mslot_c >= NRM ? mslot_c - NRM : mslot_c);
+#pragma unroll
+                    for (int w = 0; w < NW; w++) {
+                        uint32_t hn[5], ho[5];
+                        load_h(slot_n, w, hn);
+                        load_h(slot_o, w, ho);
+                        planes_addsub<PV, KH>(V[w], hn, ho);
+                    }
+                    emit(mslot_c);
+                }
+            } else {
+                // warm-up rows (window still filling) and the ragged last block
+                for (int r = 0; r < nrows; r++) {
                     int slot_n = slot0 + r;
                     slot_n = slot_n >= NR ? slot_n - NR : slot_n;
 #pragma unroll
                     for (int w = 0; w < NW; w++) {
-                        uint4 qv = Hq[(slot_n * NW + w) * HROW + lane];
-                        uint32_t h[5] = {qv.x, qv.y, qv.z, qv.w, 0};
-                        if (KH > 4) h[4] = H5[(slot_n * NW + w) * HROW + lane];
-                        planes_add<PV, KH>(V[w], h);
+                        uint32_t hn[5];
+                        load_h(slot_n, w, hn);
+                        planes_add<PV, KH>(V[w], hn);
                     }
-                    const int j = p0 + r - 2 * HALF;  // output row whose window is now complete
-                    if (j >= ja) {
-                        if (j > ja) {
+                    const int pr = p0 + r;
+                    if (pr >= first_out) {
+                        if (pr > first_out) {
                             int slot_o = slot_n - N;  // padded row j-1 left the window
                             slot_o = slot_o < 0 ? slot_o + NR : slot_o;
 #pragma unroll
                             for (int w = 0; w < NW; w++) {
-                                uint4 qv = Hq[(slot_o * NW + w) * HROW + lane];
-                                uint32_t h[5] = {qv.x, qv.y, qv.z, qv.w, 0};
-                                if (KH > 4) h[4] = H5[(slot_o * NW + w) * HROW + lane];
-                                planes_sub<PV, KH>(V[w], h);
+                                uint32_t ho[5];
+                                load_h(slot_o, w, ho);
+                                planes_sub<PV, KH>(V[w], ho);
                             }
                         }
                         int mslot_c = mslot0 + r - HALF;  // centre row j + HALF
                         mslot_c = mslot_c < 0 ? mslot_c + NRM : (mslot_c >= NRM ? mslot_c - NRM : mslot_c);
-                        uint32_t M[NW], cand[NW];
-#pragma unroll
-                        for (int w = 0; w < NW; w++) {
-                            M[w] = Mq[mslot_c * MROW + lane * NW + w];
-                            cand[w] = valid[w];
-                        }
-                        int best = 0;
-#pragma unroll
-                        for (int p = PV - 1; p >= 0; p--) {
-                            uint32_t t[NW], any = 0;
-#pragma unroll
-                            for (int w = 0; w < NW; w++) {
-                                t[w] = cand[w] & V[w][p] & M[w];
-                                any |= t[w];
-                            }
-                            if (any) {
-#pragma unroll
-                                for (int w = 0; w < NW; w++) cand[w] = t[w];
-                                best |= 1 << p;
-                            }
-                        }
-                        int idx = 0;
-#pragma unroll
-                        for (int w = 0; w < NW; w++)
-                            if (cand[w]) idx = 32 * w + 31 - __clz(cand[w]);  // later words overwrite: highest lane
-                        const int web = 32 * wg0 + idx + 1;
-                        if (store_ok) {
-                            if (chunk == 0 || best >= a.h.best[orow]) {
-                                a.h.best[orow] = best;
-                                a.h.web[orow] = web;
-                            }
-                        }
-                        orow += g.W;
+                        emit(mslot_c);
                     }
                 }
             }
@@ -311,11 +398,14 @@ template <int HALF, int NW, int SEG>
 int launch_one(const HotArgs &h, int num_sms, cudaStream_t s)
 {
     using C = WS<HALF, NW, SEG>;
-    auto kern = k_bitslice<HALF, NW, SEG>;
-    static int occ_of_device[64] = {0};  // per instantiation and per device
+    // MULTI: more than one chunk of 32*NW shifts, i.e. (best, web) are merged across passes
+    const bool multi = h.g.D > 32 * NW;
+    auto kern = multi ? k_bitslice<HALF, NW, SEG, true> : k_bitslice<HALF, NW, SEG, false>;
+    static int occ_cache[2][64] = {{0}};  // per instantiation, per MULTI flavour and per device
     int dev = 0;
     SM_CUDA(cudaGetDevice(&dev));
     dev &= 63;
+    int *occ_of_device = occ_cache[multi ? 1 : 0];
     if (occ_of_device[dev] == 0) {
         SM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         int occ = 0;
@@ -348,6 +438,10 @@ constexpr int seg_for(int half, int nw) { return nw == 1 ? 16 : (half <= 5 ? 16 
 template <int NW>
 int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s)
 {
+    // experiment hook: SMB_SEG=8|16|32 overrides the walker segment for half == 4
+    static const int seg_env = getenv("SMB_SEG") ? atoi(getenv("SMB_SEG")) : 0;
+    if (half == 4 && NW == 2 && seg_env == 8) return launch_one<4, 2, 8>(h, num_sms, s);
+    if (half == 4 && NW == 2 && seg_env == 32) return launch_one<4, 2, 32>(h, num_sms, s);
     switch (half) {
 #define SM_CASE(HF) \
     case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s);
