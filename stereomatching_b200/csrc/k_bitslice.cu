@@ -137,52 +137,48 @@ __device__ __forceinline__ void planes_addsub(uint32_t (&V)[PV], const uint32_t 
     }
 }
 
-// What a walker needs from the packed planes of its row: 96 bits of RB starting at its
-// first pixel's first shift, and 64 bits each of LA / LB starting at its first pixel.
-struct WalkIn {
-    uint32_t q0, q1, q2;  // RB window
-    uint32_t a0, a1;      // LA window
-    uint32_t b0, b1;      // LB window
+// What a walker needs from the packed planes of its row, as raw words: 96 bits of RB starting
+// at its first pixel's first shift and 64 bits each of LA / LB starting at its first pixel
+// (plus the alignment slack).  Kept raw across pass B so that the loads stay in flight; the
+// funnel shifts that align them run only when the walk starts.
+struct WalkRaw {
+    uint32_t r[4], a[3], b[3];
 };
 
-__device__ __forceinline__ WalkIn load_walk_in(const HotArgs &h, int pr, int rbit, int lbit)
+__device__ __forceinline__ void load_walk_raw(WalkRaw &o, const HotArgs &h, int pr, int rbit, int lbit)
 {
-    WalkIn o;
     const size_t row = (size_t)pr * h.g.WPR;
     const uint32_t *pq = h.RB + row + (rbit >> 5);
-    const uint32_t r0 = __ldg(pq), r1 = __ldg(pq + 1), r2 = __ldg(pq + 2), r3 = __ldg(pq + 3);
-    const int rs = rbit & 31;
-    o.q0 = __funnelshift_r(r0, r1, rs);
-    o.q1 = __funnelshift_r(r1, r2, rs);
-    o.q2 = __funnelshift_r(r2, r3, rs);
     const uint32_t *pa = h.LA + row + (lbit >> 5), *pb = h.LB + row + (lbit >> 5);
-    const uint32_t x0 = __ldg(pa), x1 = __ldg(pa + 1), x2 = __ldg(pa + 2);
-    const uint32_t y0 = __ldg(pb), y1 = __ldg(pb + 1), y2 = __ldg(pb + 2);
-    const int ls = lbit & 31;
-    o.a0 = __funnelshift_r(x0, x1, ls);
-    o.a1 = __funnelshift_r(x1, x2, ls);
-    o.b0 = __funnelshift_r(y0, y1, ls);
-    o.b1 = __funnelshift_r(y1, y2, ls);
-    return o;
+#pragma unroll
+    for (int k = 0; k < 4; k++) o.r[k] = __ldg(pq + k);
+#pragma unroll
+    for (int k = 0; k < 3; k++) o.a[k] = __ldg(pa + k), o.b[k] = __ldg(pb + k);
+}
+
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t x, uint32_t y, uint32_t z)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(x), "r"(y), "r"(z), "n"(LUT));
+    return r;
 }
 
 // One walk of pass A.  VALID_ALL: every pixel of the walk is inside the image (always so in
 // WRAP mode and away from the borders in GHOST mode), so the validity select drops out.
 template <int HALF, int NW, int SEG, bool VALID_ALL>
-__device__ __forceinline__ void walk(const WalkIn &in, uint4 *hq, uint32_t *h5, uint32_t *mq)
+__device__ __forceinline__ void walk(const uint32_t (&q)[3], const uint32_t (&lw)[2], const uint32_t (&vw)[2],
+                                     uint4 *hq, uint32_t *h5, uint32_t *mq)
 {
     using C = WS<HALF, NW, SEG>;
     constexpr int N = C::N, KH = C::KH, STEPS = C::STEPS;
-    const uint32_t q[3] = {in.q0, in.q1, in.q2};
-    const uint32_t lw[2] = {in.a0, in.a1};
-    const uint32_t vw[2] = {in.a0 | in.b0, in.a1 | in.b1};
     uint32_t P[5] = {0, 0, 0, 0, 0};
     uint32_t m[STEPS];
 #pragma unroll
     for (int t = 0; t < STEPS; t++) {
         const int qi = t >> 5;
         uint32_t mm = __funnelshift_r(q[qi], q[qi + 1 > 2 ? 2 : qi + 1], t & 31);
-        if (!(lw[t >> 5] & (1u << (t & 31)))) mm = ~mm;           // L(u) ? R : ~R
+        if (!(lw[t >> 5] & (1u << (t & 31)))) mm = ~mm;               // L(u) ? R : ~R
         if (!VALID_ALL && !(vw[t >> 5] & (1u << (t & 31)))) mm = 0u;  // taps outside the image count nothing
         m[t] = mm;
         const uint32_t mout = t >= N ? m[t - N] : 0u;
@@ -201,6 +197,59 @@ __device__ __forceinline__ void walk(const WalkIn &in, uint4 *hq, uint32_t *h5, 
         }
         if (t >= HALF && t < HALF + SEG) mq[(t - HALF) * NW] = mm;  // centre word of pixel ws*SEG + t - HALF
     }
+}
+
+// Winner-take-all of NR_ output rows at once.  The rows are independent, so interleaving
+// their bit-serial chains (AND -> test -> select, PV times) gives the scheduler NR_ chains
+// to overlap.  The selects are predicated multiply-adds on purpose: ptxas puts them on the
+// FMA pipe, which is otherwise idle, instead of the ALU pipe that carries all the LOP3 work.
+template <int NR_, int NW, int PV>
+__device__ __forceinline__ void wta(const uint32_t (&V)[NR_][NW][PV], const uint32_t (&M)[NR_][NW],
+                                    const uint32_t (&valid)[NW], int one, int (&best)[NR_], int (&idx)[NR_])
+{
+    uint32_t cand[NR_][NW];
+#pragma unroll
+    for (int k = 0; k < NR_; k++) {
+        best[k] = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) cand[k][w] = valid[w];
+    }
+#pragma unroll
+    for (int p = PV - 1; p >= 0; p--) {
+#pragma unroll
+        for (int k = 0; k < NR_; k++) {
+            uint32_t t[NW], any = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                t[w] = lop3<0x80>(cand[k][w], V[k][w][p], M[k][w]);
+                any |= t[w];
+            }
+            if (NW == 2) {
+                asm("{ .reg .pred q; setp.ne.u32 q, %3, 0;\n\t"
+                    "@q mad.lo.u32 %0, %4, %6, 0;\n\t@q mad.lo.u32 %1, %5, %6, 0;\n\t@q mad.lo.s32 %2, %6, %7, %2; }"
+                    : "+r"(cand[k][0]), "+r"(cand[k][NW - 1]), "+r"(best[k])
+                    : "r"(any), "r"(t[0]), "r"(t[NW - 1]), "r"(one), "r"(1 << p));
+            } else {
+                asm("{ .reg .pred q; setp.ne.u32 q, %2, 0;\n\t"
+                    "@q mad.lo.u32 %0, %3, %4, 0;\n\t@q mad.lo.s32 %1, %4, %5, %1; }"
+                    : "+r"(cand[k][0]), "+r"(best[k])
+                    : "r"(any), "r"(t[0]), "r"(one), "r"(1 << p));
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NR_; k++) {
+        idx[k] = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++)
+            if (cand[k][w]) idx[k] = 32 * w + 31 - __clz(cand[k][w]);  // later words overwrite: highest lane
+    }
+}
+
+__device__ __forceinline__ void store_if(int32_t *p, int v, bool on)
+{
+    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.global.b32 [%0], %1; }" ::"l"(p), "r"(v), "r"((int)on)
+                 : "memory");
 }
 
 template <int HALF, int NW, int SEG, bool MULTI>
@@ -247,6 +296,7 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
             int lanes = g.D - 32 * (wg0 + w);
             valid[w] = lanes >= 32 ? 0xFFFFFFFFu : (lanes <= 0 ? 0u : ((1u << lanes) - 1u));
         }
+        const int one = valid[0] ? 1 : g.W;  // always 1 (word 0 of a chunk has lanes); opaque to ptxas
         uint32_t V[NW][PV];
 #pragma unroll
         for (int w = 0; w < NW; w++) {
@@ -258,56 +308,27 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
             if (KH > 4) H5[((NR - 1) * NW + w) * HROW + lane] = 0u;
         }
 
-        WalkIn in = {};
-        if (ja + wr < last_pr) in = load_walk_in(a.h, ja + wr, rbit, lbit);
+        WalkRaw in = {};
+        if (ja + wr < last_pr) load_walk_raw(in, a.h, ja + wr, rbit, lbit);
         int slot0 = 0, mslot0 = 0;  // ring slots of padded row p0
-        size_t orow = (size_t)(a.h.row0 + ja) * g.W + ximg;  // output offset of the next row to be written
+        int32_t *pbest = a.h.best + (size_t)(a.h.row0 + ja) * g.W + ximg;  // next output row
+        int32_t *pweb = a.h.web + (size_t)(a.h.row0 + ja) * g.W + ximg;
 
-        // one output row: V holds the window sums of row j; pick the winner and store it
-        auto emit = [&](int mslot_c) {
-            uint32_t M[NW], cand[NW];
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                M[w] = Mq[mslot_c * MROW + lane * NW + w];
-                cand[w] = valid[w];
-            }
-            int best = 0;
-            const int one = valid[0] ? 1 : g.W;  // always 1 (shift word 0 of a chunk has lanes); opaque to ptxas
-#pragma unroll
-            for (int p = PV - 1; p >= 0; p--) {
-                uint32_t t[NW], any = 0;
-#pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    t[w] = cand[w] & V[w][p] & M[w];
-                    any |= t[w];
-                }
-                // predicated moves / multiply-add: ptxas places these on the FMA pipe, which is
-                // otherwise idle (the ALU pipe carries all the LOP3 work)
-                if (NW == 2) {
-                    asm("{ .reg .pred q; setp.ne.u32 q, %3, 0;\n\t"
-                        "@q mad.lo.u32 %0, %4, %6, 0;\n\t@q mad.lo.u32 %1, %5, %6, 0;\n\t@q mad.lo.s32 %2, %6, %7, %2; }"
-                        : "+r"(cand[0]), "+r"(cand[NW - 1]), "+r"(best)
-                        : "r"(any), "r"(t[0]), "r"(t[NW - 1]), "r"(one), "r"(1 << p));
-                } else {
-                    asm("{ .reg .pred q; setp.ne.u32 q, %2, 0;\n\t"
-                        "@q mad.lo.u32 %0, %3, %4, 0;\n\t@q mad.lo.s32 %1, %4, %5, %1; }"
-                        : "+r"(cand[0]), "+r"(best)
-                        : "r"(any), "r"(t[0]), "r"(one), "r"(1 << p));
-                }
-            }
-            int idx = 0;
-#pragma unroll
-            for (int w = 0; w < NW; w++)
-                if (cand[w]) idx = 32 * w + 31 - __clz(cand[w]);  // later words overwrite: highest lane
+        // store NR_ finished rows (best, idx) and advance the output pointers
+        auto put = [&](int best, int idx) {
             const int web = 32 * wg0 + idx + 1;
             bool st = store_ok;
-            if (MULTI && chunk != 0 && st) st = best >= a.h.best[orow];  // a later chunk wins ties (higher shifts)
-            if (st) {
-                a.h.best[orow] = best;
-                a.h.web[orow] = web;
-            }
-            orow += g.W;
+            if (MULTI && chunk != 0 && st) st = best >= *pbest;  // a later chunk wins ties (higher shifts)
+            store_if(pbest, best, st);
+            store_if(pweb, web, st);
+            pbest += g.W;
+            pweb += g.W;
         };
+        auto load_m = [&](int mslot_c, uint32_t (&M)[NW]) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) M[w] = Mq[mslot_c * MROW + lane * NW + w];
+        };
+        auto wrap_m = [&](int ms) { return ms < 0 ? ms + NRM : (ms >= NRM ? ms - NRM : ms); };
 
         for (int p0 = ja; p0 < last_pr; p0 += RB) {
             const int nrows = min(RB, last_pr - p0);
@@ -322,39 +343,54 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
                 uint4 *hq = Hq + (slot * NW + ww) * HROW + ws * SEG;
                 uint32_t *h5 = H5 + (slot * NW + ww) * HROW + ws * SEG;
                 uint32_t *mq = Mq + mslot * MROW + (ws * SEG) * NW + ww;
-                const unsigned long long vl =
-                    (((unsigned long long)(in.a1 | in.b1)) << 32) | (in.a0 | in.b0);
+                const int rs = rbit & 31, ls = lbit & 31;
+                const uint32_t q[3] = {__funnelshift_r(in.r[0], in.r[1], rs), __funnelshift_r(in.r[1], in.r[2], rs),
+                                       __funnelshift_r(in.r[2], in.r[3], rs)};
+                const uint32_t lw[2] = {__funnelshift_r(in.a[0], in.a[1], ls), __funnelshift_r(in.a[1], in.a[2], ls)};
+                const uint32_t bw[2] = {__funnelshift_r(in.b[0], in.b[1], ls), __funnelshift_r(in.b[1], in.b[2], ls)};
+                const uint32_t vw[2] = {lw[0] | bw[0], lw[1] | bw[1]};
+                const unsigned long long vl = (((unsigned long long)vw[1]) << 32) | vw[0];
                 const bool all_valid = (~vl & ((1ull << STEPS) - 1ull)) == 0ull;
                 if (__all_sync(0xFFFFFFFFu, all_valid || !active)) {
-                    if (active) walk<HALF, NW, SEG, true>(in, hq, h5, mq);
+                    if (active) walk<HALF, NW, SEG, true>(q, lw, vw, hq, h5, mq);
                 } else {
-                    if (active) walk<HALF, NW, SEG, false>(in, hq, h5, mq);
+                    if (active) walk<HALF, NW, SEG, false>(q, lw, vw, hq, h5, mq);
                 }
             }
             __syncwarp();
 
             // prefetch the next block's walker inputs; they land while pass B runs
-            if (p0 + RB + wr < last_pr) in = load_walk_in(a.h, p0 + RB + wr, rbit, lbit);
+            if (p0 + RB + wr < last_pr) load_walk_raw(in, a.h, p0 + RB + wr, rbit, lbit);
 
             // ---------------- pass B: 32 pixel columns ----------------
             if (p0 >= first_out && nrows == RB) {
-                // steady state, branch-free: every row enters, one leaves, one output row
+                // steady state, branch-free: every row enters, one leaves, one output row.
+                // Rows go in groups of G so that their winner-take-all chains interleave.
+                constexpr int G = (RB % 2 == 0) ? 2 : 1;
 #pragma unroll
-                for (int r = 0; r < RB; r++) {
-                    int slot_n = slot0 + r;
-                    slot_n = slot_n >= NR ? slot_n - NR : slot_n;
-                    int slot_o = slot_n - N;
-                    slot_o = slot_o < 0 ? slot_o + NR : slot_o;
-                    int mslot_c = mslot0 + r - HALF;
-                    mslot_c = mslot_c < 0 ? mslot_c + NRM : (mslot_c >= NRM ? mslot_c - NRM : mslot_c);
+                for (int r = 0; r < RB; r += G) {
+                    uint32_t Vs[G][NW][PV], Ms[G][NW];
 #pragma unroll
-                    for (int w = 0; w < NW; w++) {
-                        uint32_t hn[5], ho[5];
-                        load_h(slot_n, w, hn);
-                        load_h(slot_o, w, ho);
-                        planes_addsub<PV, KH>(V[w], hn, ho);
+                    for (int k = 0; k < G; k++) {
+                        int slot_n = slot0 + r + k;
+                        slot_n = slot_n >= NR ? slot_n - NR : slot_n;
+                        int slot_o = slot_n - N;
+                        slot_o = slot_o < 0 ? slot_o + NR : slot_o;
+#pragma unroll
+                        for (int w = 0; w < NW; w++) {
+                            uint32_t hn[5], ho[5];
+                            load_h(slot_n, w, hn);
+                            load_h(slot_o, w, ho);
+                            planes_addsub<PV, KH>(V[w], hn, ho);
+#pragma unroll
+                            for (int p = 0; p < PV; p++) Vs[k][w][p] = V[w][p];
+                        }
+                        load_m(wrap_m(mslot0 + r + k - HALF), Ms[k]);
                     }
-                    emit(mslot_c);
+                    int best[G], idx[G];
+                    wta<G, NW, PV>(Vs, Ms, valid, one, best, idx);
+#pragma unroll
+                    for (int k = 0; k < G; k++) put(best[k], idx[k]);
                 }
             } else {
                 // warm-up rows (window still filling) and the ragged last block
@@ -379,9 +415,15 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
                                 planes_sub<PV, KH>(V[w], ho);
                             }
                         }
-                        int mslot_c = mslot0 + r - HALF;  // centre row j + HALF
-                        mslot_c = mslot_c < 0 ? mslot_c + NRM : (mslot_c >= NRM ? mslot_c - NRM : mslot_c);
-                        emit(mslot_c);
+                        uint32_t Vs[1][NW][PV], Ms[1][NW];
+#pragma unroll
+                        for (int w = 0; w < NW; w++)
+#pragma unroll
+                            for (int p = 0; p < PV; p++) Vs[0][w][p] = V[w][p];
+                        load_m(wrap_m(mslot0 + r - HALF), Ms[0]);  // centre row j + HALF
+                        int best[1], idx[1];
+                        wta<1, NW, PV>(Vs, Ms, valid, one, best, idx);
+                        put(best[0], idx[0]);
                     }
                 }
             }
