@@ -150,6 +150,16 @@ int sm_match_wta(sm_ctx *ctx);
 int sm_match_wta_dev(sm_ctx *ctx, const uint8_t *d_first_edges, const uint8_t *d_second_edges,
                      int32_t *d_best, int32_t *d_web);
 
+/* The same for n_pairs resident pairs in one call: pair k's edge maps are at
+ * d_*_edges + k*edge_stride (elements), its outputs at d_best/d_web + k*out_stride.
+ * All inputs must be ready in stream order when the call is made.  Inside, a second
+ * stream runs the bit-plane pack of pair k+1.. while the main kernel of pair k runs, so
+ * per pair only the main kernel's time shows (whole-pair batches).
+ * Results are complete in stream order on the context's stream. */
+int sm_match_wta_dev_batch(sm_ctx *ctx, int n_pairs, const uint8_t *d_first_edges,
+                           const uint8_t *d_second_edges, size_t edge_stride, int32_t *d_best,
+                           int32_t *d_web, size_t out_stride);
+
 /* Device time of the last sm_match_wta* call on this context, CUDA events on the
  * context's stream (the reference brackets the whole algorithm() with
  * CLOCK_MONOTONIC instead, stereo.cu:308,334-335).  Waits for the call to finish. */

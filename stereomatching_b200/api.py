@@ -27,7 +27,7 @@ SYMBOLS = [
     "sm_last_error", "sm_version", "sm_device_count", "sm_host_alloc", "sm_host_free",
     "sm_create", "sm_create_band", "sm_destroy", "sm_set_stream", "sm_set_kernel",
     "sm_synchronize", "sm_upload_f64", "sm_upload_u8", "sm_edges", "sm_set_edges",
-    "sm_match_wta", "sm_match_wta_dev", "sm_elapsed_ms", "sm_last_launches",
+    "sm_match_wta", "sm_match_wta_dev", "sm_match_wta_dev_batch", "sm_elapsed_ms", "sm_last_launches",
     "sm_profile_begin", "sm_profile_read", "sm_measure_int_peak",
     "sm_fill_web_holes", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
     "sm_run_batch", "sm_band_rows",
@@ -66,6 +66,7 @@ def lib() -> C.CDLL:
         L.sm_set_edges.argtypes = [vp, vp, vp]
         L.sm_match_wta.argtypes = [vp]
         L.sm_match_wta_dev.argtypes = [vp, vp, vp, vp, vp]
+        L.sm_match_wta_dev_batch.argtypes = [vp, i, vp, vp, C.c_size_t, vp, vp, C.c_size_t]
         L.sm_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.sm_last_launches.argtypes = [vp]
         L.sm_profile_begin.argtypes = [vp, i]
@@ -203,6 +204,12 @@ class StereoContext:
     def match_wta_dev(self, d_first_edges: int, d_second_edges: int, d_best: int, d_web: int):
         _check(lib().sm_match_wta_dev(self._c, C.c_void_p(d_first_edges), C.c_void_p(d_second_edges),
                                       C.c_void_p(d_best), C.c_void_p(d_web)))
+
+    def match_wta_dev_batch(self, n_pairs: int, d_first_edges: int, d_second_edges: int, edge_stride: int,
+                            d_best: int, d_web: int, out_stride: int):
+        """n_pairs resident pairs, strides in elements; pack of pair k+1 overlaps the main kernel of pair k."""
+        _check(lib().sm_match_wta_dev_batch(self._c, n_pairs, C.c_void_p(d_first_edges), C.c_void_p(d_second_edges),
+                                            edge_stride, C.c_void_p(d_best), C.c_void_p(d_web), out_stride))
 
     def elapsed_ms(self) -> float:
         ms = C.c_float()

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
             if (p0 >= first_out && nrows == RB) {
                 // steady state, branch-free: every row enters, one leaves, one output row.
                 // Rows go in groups of G so that their winner-take-all chains interleave.
-                constexpr int G = (RB % 2 == 0) ? 2 : 1;
+                constexpr int G = (RB % 4 == 0) ? 4 : ((RB % 2 == 0) ? 2 : 1);
 #pragma unroll
                 for (int r = 0; r < RB; r += G) {
                     uint32_t Vs[G][NW][PV], Ms[G][NW];

@@ -60,6 +60,15 @@ struct sm_ctx {
     int32_t *minmax = nullptr;
     // band-sized packed planes
     uint32_t *LA = nullptr, *LB = nullptr, *RB = nullptr;
+    // sm_match_wta_dev_batch: a second stream packs pair k+1.. while the main kernel of
+    // pair k runs; NPB packed-plane sets rotate between the two
+    static constexpr int NPB = 3;
+    cudaStream_t pack_stream = nullptr, main2_stream = nullptr;  // main kernels alternate stream / main2_stream
+    cudaEvent_t ev_join = nullptr;
+    uint32_t *pLA[NPB] = {nullptr, nullptr, nullptr}, *pLB[NPB] = {nullptr, nullptr, nullptr},
+             *pRB[NPB] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_packed[NPB] = {nullptr, nullptr, nullptr}, ev_used[NPB] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr;
     // scratch for on-demand debug planes / u8 web
     uint8_t *scratch_u8 = nullptr;
     int32_t *scratch_i32 = nullptr;
@@ -176,6 +185,20 @@ HotArgs hot_args(sm_ctx *c, int32_t *best, int32_t *web)
     return a;
 }
 
+int launch_main(sm_ctx *c, const HotArgs &a, cudaStream_t st)
+{
+    int k = c->kernel;
+    if (k == SM_KERNEL_AUTO) k = bitslice_supports(c->half, c->D) ? SM_KERNEL_BITSLICE : SM_KERNEL_DIRECT;
+    if (k == SM_KERNEL_BITSLICE) {
+        if (!bitslice_supports(c->half, c->D)) {
+            set_error("bit-sliced kernel does not cover square_width %d / num_shifts %d", c->sw, c->D);
+            return SM_ERR_ARG;
+        }
+        return launch_bitslice(a, c->num_sms, st);
+    }
+    return launch_direct(a, st);
+}
+
 int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int32_t *web)
 {
     int launches = 0, rc;
@@ -187,17 +210,7 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
     launches += rc;
     if (pe) SM_CUDA(cudaEventRecord(pe[1], c->stream));
     HotArgs a = hot_args(c, best, web);
-    int k = c->kernel;
-    if (k == SM_KERNEL_AUTO) k = bitslice_supports(c->half, c->D) ? SM_KERNEL_BITSLICE : SM_KERNEL_DIRECT;
-    if (k == SM_KERNEL_BITSLICE) {
-        if (!bitslice_supports(c->half, c->D)) {
-            set_error("bit-sliced kernel does not cover square_width %d / num_shifts %d", c->sw, c->D);
-            return SM_ERR_ARG;
-        }
-        rc = launch_bitslice(a, c->num_sms, c->stream);
-    } else {
-        rc = launch_direct(a, c->stream);
-    }
+    rc = launch_main(c, a, c->stream);
     if (rc < 0) return rc;
     launches += rc;
     SM_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -341,6 +354,23 @@ extern "C" int sm_destroy(sm_ctx *c)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->prof_ev) profile_free(c);
+    if (c->pack_stream) {
+        cudaStreamSynchronize(c->pack_stream);
+        cudaStreamDestroy(c->pack_stream);
+    }
+    if (c->main2_stream) {
+        cudaStreamSynchronize(c->main2_stream);
+        cudaStreamDestroy(c->main2_stream);
+    }
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (int k = 0; k < sm_ctx::NPB; k++) {
+        if (c->pLA[k]) cudaFree(c->pLA[k]);
+        if (c->pLB[k]) cudaFree(c->pLB[k]);
+        if (c->pRB[k]) cudaFree(c->pRB[k]);
+        if (c->ev_packed[k]) cudaEventDestroy(c->ev_packed[k]);
+        if (c->ev_used[k]) cudaEventDestroy(c->ev_used[k]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -476,6 +506,75 @@ extern "C" int sm_match_wta_dev(sm_ctx *c, const uint8_t *d_first_edges, const u
     SM_ENTER(c);
     SM_REQUIRE(d_first_edges && d_second_edges && d_best && d_web, "sm_match_wta_dev: NULL pointer");
     return run_hot(c, d_first_edges, d_second_edges, d_best, d_web);
+}
+
+extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_first_edges,
+                                      const uint8_t *d_second_edges, size_t edge_stride, int32_t *d_best,
+                                      int32_t *d_web, size_t out_stride)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(n_pairs >= 0 && d_first_edges && d_second_edges && d_best && d_web,
+               "sm_match_wta_dev_batch: bad arguments");
+    SM_REQUIRE(edge_stride >= c->npix() && out_stride >= c->npix(), "sm_match_wta_dev_batch: stride below frame size");
+    constexpr int NPB = sm_ctx::NPB;
+    if (!c->pack_stream) {
+        SM_CUDA(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
+        SM_CUDA(cudaStreamCreateWithFlags(&c->main2_stream, cudaStreamNonBlocking));
+        SM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        SM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        const size_t pw = (size_t)c->g.ER * c->g.WPR;
+        for (int k = 0; k < NPB; k++) {
+            int rc;
+            if ((rc = dev_alloc(&c->pLA[k], pw)) || (rc = dev_alloc(&c->pLB[k], pw)) || (rc = dev_alloc(&c->pRB[k], pw)))
+                return rc;
+            SM_CUDA(cudaEventCreateWithFlags(&c->ev_packed[k], cudaEventDisableTiming));
+            SM_CUDA(cudaEventCreateWithFlags(&c->ev_used[k], cudaEventDisableTiming));
+        }
+    }
+    // everything queued on the context's stream so far (the producers of the edge maps) comes first
+    SM_CUDA(cudaEventRecord(c->ev0, c->stream));
+    SM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    SM_CUDA(cudaStreamWaitEvent(c->pack_stream, c->ev_fork, 0));
+    SM_CUDA(cudaStreamWaitEvent(c->main2_stream, c->ev_fork, 0));
+    int launches = 0;
+    for (int k = 0; k < n_pairs; k++) {
+        const int b = k % NPB;
+        int rc;
+        if (k >= NPB) SM_CUDA(cudaStreamWaitEvent(c->pack_stream, c->ev_used[b], 0));  // main(k - NPB) is done with set b
+        rc = launch_pack(d_first_edges + (size_t)k * edge_stride, d_second_edges + (size_t)k * edge_stride, c->FH,
+                         c->row0, c->variant, c->g, c->pLA[b], c->pLB[b], c->pRB[b], c->pack_stream);
+        if (rc < 0) return rc;
+        launches += rc;
+        SM_CUDA(cudaEventRecord(c->ev_packed[b], c->pack_stream));
+        // consecutive pairs are independent: alternate two streams so that the next main
+        // kernel's CTAs fill the SM slots the previous one frees (no tail / ramp between pairs)
+        cudaStream_t ms = (k & 1) ? c->main2_stream : c->stream;
+        SM_CUDA(cudaStreamWaitEvent(ms, c->ev_packed[b], 0));
+        cudaEvent_t *pe = (c->prof_ev && c->prof_n < c->prof_cap) ? c->prof_ev + 3 * c->prof_n : nullptr;
+        if (pe) {
+            SM_CUDA(cudaEventRecord(pe[0], ms));  // pack runs on the other stream: not timed here
+            SM_CUDA(cudaEventRecord(pe[1], ms));
+        }
+        HotArgs a = hot_args(c, d_best + (size_t)k * out_stride, d_web + (size_t)k * out_stride);
+        a.LA = c->pLA[b];
+        a.LB = c->pLB[b];
+        a.RB = c->pRB[b];
+        rc = launch_main(c, a, ms);
+        if (rc < 0) return rc;
+        launches += rc;
+        if (pe) {
+            SM_CUDA(cudaEventRecord(pe[2], ms));
+            c->prof_n++;
+        }
+        SM_CUDA(cudaEventRecord(c->ev_used[b], ms));
+    }
+    // join: the context's stream is complete only when both main streams are
+    SM_CUDA(cudaEventRecord(c->ev_join, c->main2_stream));
+    SM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    SM_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    c->last_launches = launches;
+    return SM_OK;
 }
 
 extern "C" int sm_elapsed_ms(sm_ctx *c, float *ms)

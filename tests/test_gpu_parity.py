@@ -279,6 +279,28 @@ def test_device_pointer_entry_with_torch(orc):
     assert np.array_equal(best.cpu().numpy(), bo) and np.array_equal(web.cpu().numpy(), wo)
 
 
+def test_device_batch_entry_overlapped_pack(orc):
+    """sm_match_wta_dev_batch: pack of pair k+1 on a second stream; more pairs than plane sets."""
+    torch = pytest.importorskip("torch")
+    n, w, h, D, sw = 7, 200, 90, 64, 9
+    pairs = [orc.synth_pair(500 + k, w, h, D) for k in range(n)]
+    for variant in (smb.WRAP, smb.GHOST):
+        e1 = np.stack([orc.edges(p[0], THRESHOLD, variant) for p in pairs])
+        e2 = np.stack([orc.edges(p[1], THRESHOLD, variant) for p in pairs])
+        d1, d2 = torch.from_numpy(e1).cuda(), torch.from_numpy(e2).cuda()
+        best = torch.full((n, h, w), -7, dtype=torch.int32, device="cuda")
+        web = torch.full((n, h, w), -7, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        with _ctx(w, h, D, sw, variant) as c:
+            c.set_stream(torch.cuda.current_stream().cuda_stream)
+            for _ in range(2):  # second call reuses the rotating plane sets
+                c.match_wta_dev_batch(n, d1.data_ptr(), d2.data_ptr(), h * w, best.data_ptr(), web.data_ptr(), h * w)
+            torch.cuda.synchronize()
+        for k in range(n):
+            bo, wo = orc.match_wta(e1[k], e2[k], D, sw, variant)
+            assert np.array_equal(best[k].cpu().numpy(), bo) and np.array_equal(web[k].cpu().numpy(), wo), k
+
+
 # ---------------------------------------------------------------------------------
 # full-size properties (sizes the CPU oracle cannot finish in seconds)
 # ---------------------------------------------------------------------------------
