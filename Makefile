@@ -34,7 +34,7 @@ CSRC   := stereomatching_b200/csrc
 LIB    := stereomatching_b200/libstereo_b200.so
 KOBJS  := $(patsubst %,$(CSRC)/build/%.o,stereo_b200 k_edges k_pack k_direct k_bitslice k_step3 k_peak)
 
-all: lib $(outdir)/stereopar $(outdir)/stereopar-ghost
+all: lib $(outdir)/stereopar $(outdir)/stereopar-ghost host/libhostimage.so
 
 lib: $(LIB)
 
@@ -56,6 +56,10 @@ $(outdir)/stereopar: host/driver.c host/hostimage.c host/hostimage.h include/ste
 $(outdir)/stereopar-ghost: host/driver.c host/hostimage.c host/hostimage.h include/stereo_b200.h $(LIB) | $(outdir)
 	$(CC) $(CFLAGS) -DSM_VARIANT=1 host/driver.c host/hostimage.c -o $@ \
 	    -Lstereomatching_b200 -lstereo_b200 -Wl,-rpath,'$$ORIGIN/../stereomatching_b200' -lz -lm
+
+# hostimage as a shared object, for the CPU tests of the PNG reader / PPM writer
+host/libhostimage.so: host/hostimage.c host/hostimage.h
+	$(CC) -Wall -Wextra -std=gnu11 -O2 -fPIC -shared host/hostimage.c -o $@ -lz
 
 oracle:
 	$(MAKE) -C oracle liboracle.so
