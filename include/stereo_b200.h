@@ -187,6 +187,11 @@ int sm_measure_int_peak(int device, int mode, double *gops_per_s);
 /* Replaces the D2D copy + fill_web_holes() (stereo.cu:328-329 -> :247-259, kernel
  * :235-245). */
 int sm_fill_web_holes(sm_ctx *ctx, int times);
+/* Step 3 on a caller-supplied web (host array, i32, may contain 0 = "hole"): the entry for
+ * using fill_web_holes / draw_contour_map on their own (the web sm_match_wta produces never
+ * has holes, so for it sm_fill_web_holes is the identity and launches nothing). */
+int sm_set_web(sm_ctx *ctx, const int32_t *web);
+
 /* Replaces draw_contour_map() (stereo.cu:331 -> :276-285, kernel :261-274) and the
  * array_max_gpu/array_min_gpu reductions (util.cu:15-45).  web_min / web_max may be
  * NULL.  Returns SM_ERR_DEGENERATE when (max-min)/lines == 0. */

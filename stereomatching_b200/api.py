@@ -29,7 +29,7 @@ SYMBOLS = [
     "sm_synchronize", "sm_upload_f64", "sm_upload_u8", "sm_edges", "sm_set_edges",
     "sm_match_wta", "sm_match_wta_dev", "sm_match_wta_dev_batch", "sm_elapsed_ms", "sm_last_launches",
     "sm_profile_begin", "sm_profile_read", "sm_measure_int_peak",
-    "sm_fill_web_holes", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
+    "sm_fill_web_holes", "sm_set_web", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
     "sm_run_batch", "sm_band_rows",
 ]
 
@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
         L.sm_profile_read.argtypes = [vp, C.POINTER(i), C.POINTER(d), C.POINTER(d)]
         L.sm_measure_int_peak.argtypes = [i, i, C.POINTER(d)]
         L.sm_fill_web_holes.argtypes = [vp, i]
+        L.sm_set_web.argtypes = [vp, vp]
         L.sm_draw_contour_map.argtypes = [vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.sm_download.argtypes = [vp, i, i, vp]
         L.sm_download_web_u8.argtypes = [vp, vp]
@@ -227,6 +228,11 @@ class StereoContext:
         n, p, m = C.c_int(), C.c_double(), C.c_double()
         _check(lib().sm_profile_read(self._c, C.byref(n), C.byref(p), C.byref(m)))
         return n.value, p.value, m.value
+
+    def set_web(self, web):
+        a = self._frame(web, np.int32)
+        _check(lib().sm_set_web(self._c, _ptr(a)))
+        self.synchronize()
 
     def fill_web_holes(self, times=32):
         _check(lib().sm_fill_web_holes(self._c, times))

@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
 }
 
 template <int HALF, int NW, int SEG>
-int launch_one(const HotArgs &h, int num_sms, cudaStream_t s)
+int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
 {
     using C = WS<HALF, NW, SEG>;
     // MULTI: more than one chunk of 32*NW shifts, i.e. (best, web) are merged across passes
@@ -454,6 +454,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s)
         SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, C::SMEM));
         occ_of_device[dev] = occ > 0 ? occ : 1;
     }
+    if (prepare_only) return 0;  // module loaded, attribute set, occupancy cached
     const int blocks_per_sm = occ_of_device[dev];
     BitsliceArgs a;
     a.h = h;
@@ -478,15 +479,15 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s)
 constexpr int seg_for(int half, int nw) { return nw == 1 ? 16 : (half <= 5 ? 16 : 32); }
 
 template <int NW>
-int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s)
+int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
 {
     // experiment hook: SMB_SEG=8|16|32 overrides the walker segment for half == 4
     static const int seg_env = getenv("SMB_SEG") ? atoi(getenv("SMB_SEG")) : 0;
-    if (half == 4 && NW == 2 && seg_env == 8) return launch_one<4, 2, 8>(h, num_sms, s);
-    if (half == 4 && NW == 2 && seg_env == 32) return launch_one<4, 2, 32>(h, num_sms, s);
+    if (half == 4 && NW == 2 && seg_env == 8) return launch_one<4, 2, 8>(h, num_sms, s, prepare_only);
+    if (half == 4 && NW == 2 && seg_env == 32) return launch_one<4, 2, 32>(h, num_sms, s, prepare_only);
     switch (half) {
 #define SM_CASE(HF) \
-    case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s);
+    case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s, prepare_only);
         SM_CASE(0) SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5)
         SM_CASE(6) SM_CASE(7) SM_CASE(8) SM_CASE(9) SM_CASE(10)
 #undef SM_CASE
@@ -501,8 +502,16 @@ bool bitslice_supports(int half, int D) { return half >= 0 && half <= 10 && D >=
 
 int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
 {
-    if (h.g.D <= 32) return dispatch_half<1>(h.g.half, h, num_sms, s);
-    return dispatch_half<2>(h.g.half, h, num_sms, s);
+    if (h.g.D <= 32) return dispatch_half<1>(h.g.half, h, num_sms, s, false);
+    return dispatch_half<2>(h.g.half, h, num_sms, s, false);
+}
+
+// Loads the kernel this geometry will use, sets its shared-memory attribute and caches its
+// occupancy, so that the first sm_match_wta call pays none of that.
+int prepare_bitslice(const HotArgs &h, int num_sms)
+{
+    if (h.g.D <= 32) return dispatch_half<1>(h.g.half, h, num_sms, nullptr, true);
+    return dispatch_half<2>(h.g.half, h, num_sms, nullptr, true);
 }
 
 }  // namespace smb

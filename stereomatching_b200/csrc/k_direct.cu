@@ -97,4 +97,10 @@ int launch_planes(const HotArgs &a, int shift, uint8_t *match, int32_t *score_al
     return 1;
 }
 
+void warm_direct()
+{
+    warm_kernel(k_direct);
+    warm_kernel(k_planes);
+}
+
 }  // namespace smb

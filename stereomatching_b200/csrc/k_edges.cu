@@ -100,4 +100,124 @@ template int launch_edges<uint8_t>(const uint8_t *, int, int, int, int, int, dou
 template int launch_edges<double>(const double *, int, int, int, int, int, double, uint8_t *,
                                   cudaStream_t);
 
+// ---- integer fast path for 8-bit images -----------------------------------------------
+// With 8-bit pixels every directional detector depends only on the two integer 3-pixel
+// sums L, R in [0, 765] (each brightness is k/256 exactly, so the two additions are exact
+// and ((a+b)+c)/3.0 == fl((L/256)/3)) and on the threshold.  k_edge_lut evaluates the
+// reference's FP64 expression (stereo.c:16-28) once for all 766 x 766 pairs into a bit
+// table; k_edges_lut then needs integer adds and four table bits per pixel.  Pixels whose
+// 3x3 stencil leaves the image in the GHOST variant see the 128.0 ghost cells
+// (stereo-ghost.c:384-385), which are not 8-bit values: they take the FP64 path.
+constexpr int LUT_N = 766, LUT_WORDS = 24;  // 766 bits per row -> 24 words
+
+__global__ void __launch_bounds__(256) k_edge_lut(double thr, uint32_t *__restrict__ lut)
+{
+    const int L = blockIdx.x;
+    for (int wd = threadIdx.x; wd < LUT_WORDS; wd += blockDim.x) {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; b++) {
+            const int R = wd * 32 + b;
+            if (R < LUT_N) {
+                const double sl = __ddiv_rn((double)L, 256.0), sr = __ddiv_rn((double)R, 256.0);
+                // detect() with the sums already formed: pass them as (s, 0, 0)
+                bits |= (uint32_t)detect(sl, 0.0, 0.0, sr, 0.0, 0.0, thr) << b;
+            }
+        }
+        lut[L * LUT_WORDS + wd] = bits;
+    }
+}
+
+__device__ __forceinline__ int lut_bit(const uint32_t *__restrict__ lut, int L, int R)
+{
+    return (__ldg(lut + L * LUT_WORDS + (R >> 5)) >> (R & 31)) & 1;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256)
+k_edges_lut(const uint8_t *__restrict__ img, int W, int FH, int ystart, int nrows, double thr,
+            const uint32_t *__restrict__ lut, uint8_t *__restrict__ edges)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || r >= nrows) return;
+    int y = ystart + r;
+    if (VARIANT == SM_WRAP) {
+        y %= FH;
+        if (y < 0) y += FH;
+    } else if (y < 0 || y >= FH) {
+        return;
+    }
+    int xm = x - 1, xp = x + 1, ym = y - 1, yp = y + 1;
+    if (VARIANT == SM_WRAP) {
+        xm = xm < 0 ? xm + W : xm;
+        xp = xp >= W ? xp - W : xp;
+        ym = ym < 0 ? ym + FH : ym;
+        yp = yp >= FH ? yp - FH : yp;
+    } else if (xm < 0 || xp >= W || ym < 0 || yp >= FH) {
+        // border pixel of the GHOST variant: FP64 with the 128.0 ghost cells
+        double b[3][3];
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+                int xx = x + dx, yy = y + dy;
+                bool in = xx >= 0 && xx < W && yy >= 0 && yy < FH;
+                b[dy + 1][dx + 1] = in ? to_bright<uint8_t>(img[(size_t)yy * W + xx]) : 128.0;
+            }
+#define B(dx, dy) b[(dy) + 1][(dx) + 1]
+        int e = detect(B(-1, -1), B(-1, 0), B(-1, 1), B(1, -1), B(1, 0), B(1, 1), thr) |
+                detect(B(-1, -1), B(0, -1), B(1, -1), B(-1, 1), B(0, 1), B(1, 1), thr) |
+                detect(B(-1, -1), B(0, -1), B(-1, 0), B(1, 0), B(0, 1), B(1, 1), thr) |
+                detect(B(-1, 1), B(0, 1), B(-1, 0), B(0, -1), B(1, -1), B(1, 0), thr);
+#undef B
+        edges[(size_t)y * W + x] = (uint8_t)e;
+        return;
+    }
+    const uint8_t *r0 = img + (size_t)ym * W, *r1 = img + (size_t)y * W, *r2 = img + (size_t)yp * W;
+    const int tl = r0[xm], tc = r0[x], tr = r0[xp];
+    const int ml = r1[xm], mr = r1[xp];
+    const int bl = r2[xm], bc = r2[x], br = r2[xp];
+    int e = lut_bit(lut, tl + ml + bl, tr + mr + br)      // left_right       stereo.c:16-28
+            | lut_bit(lut, tl + tc + tr, bl + bc + br)    // top_bottom       stereo.c:30-42
+            | lut_bit(lut, tl + tc + ml, mr + bc + br)    // upleft_downright stereo.c:44-56
+            | lut_bit(lut, bl + bc + ml, tc + tr + mr);   // downleft_upright stereo.c:58-70
+    edges[(size_t)y * W + x] = (uint8_t)e;
+}
+
+int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s)
+{
+    k_edge_lut<<<LUT_N, 32, 0, s>>>(threshold, lut);
+    SM_CUDA(cudaGetLastError());
+    return 1;
+}
+
+size_t edge_lut_words() { return (size_t)LUT_N * LUT_WORDS; }
+
+int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
+                     const uint32_t *lut, uint8_t *edges, cudaStream_t s)
+{
+    dim3 block(64, 4);
+    dim3 grid((W + block.x - 1) / block.x, (nrows + block.y - 1) / block.y);
+    if (variant == SM_WRAP)
+        k_edges_lut<SM_WRAP><<<grid, block, 0, s>>>(img, W, FH, ystart, nrows, threshold, lut, edges);
+    else
+        k_edges_lut<SM_GHOST><<<grid, block, 0, s>>>(img, W, FH, ystart, nrows, threshold, lut, edges);
+    SM_CUDA(cudaGetLastError());
+    return 1;
+}
+
+void warm_edges(int variant)
+{
+    warm_kernel(k_edge_lut);
+    if (variant == SM_WRAP) {
+        warm_kernel(k_edges<uint8_t, SM_WRAP>);
+        warm_kernel(k_edges<double, SM_WRAP>);
+        warm_kernel(k_edges_lut<SM_WRAP>);
+    } else {
+        warm_kernel(k_edges<uint8_t, SM_GHOST>);
+        warm_kernel(k_edges<double, SM_GHOST>);
+        warm_kernel(k_edges_lut<SM_GHOST>);
+    }
+}
+
 }  // namespace smb

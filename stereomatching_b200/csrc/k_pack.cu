@@ -101,4 +101,12 @@ int launch_pack(const uint8_t *e1, const uint8_t *e2, int FH, int row0, int vari
     return 1;
 }
 
+void warm_pack(int variant)
+{
+    if (variant == SM_WRAP)
+        warm_kernel(k_pack<SM_WRAP>);
+    else
+        warm_kernel(k_pack<SM_GHOST>);
+}
+
 }  // namespace smb

@@ -123,4 +123,13 @@ int launch_i32_to_u8(const int32_t *src, uint8_t *dst, size_t n, cudaStream_t s)
     return 1;
 }
 
+void warm_step3()
+{
+    warm_kernel(k_fill_holes);
+    warm_kernel(k_minmax_init);
+    warm_kernel(k_minmax);
+    warm_kernel(k_contour);
+    warm_kernel(k_i32_to_u8);
+}
+
 }  // namespace smb

@@ -79,12 +79,31 @@ int launch_pack(const uint8_t *e1, const uint8_t *e2, int FH, int row0, int vari
 int launch_direct(const HotArgs &a, cudaStream_t s);
 int launch_bitslice(const HotArgs &a, int num_sms, cudaStream_t s);
 bool bitslice_supports(int half, int D);
+int prepare_bitslice(const HotArgs &a, int num_sms);
+// force the (lazily loaded) kernels of each translation unit into the context
+void warm_edges(int variant);
+void warm_pack(int variant);
+void warm_direct();
+void warm_step3();
+
+template <typename K>
+inline void warm_kernel(K k)
+{
+    cudaFuncAttributes attr;
+    (void)cudaFuncGetAttributes(&attr, k);
+}
 int launch_planes(const HotArgs &a, int shift, uint8_t *match, int32_t *score_all, int32_t *score,
                   cudaStream_t s);
 
 template <typename T>
 int launch_edges(const T *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
                  uint8_t *edges, cudaStream_t s);
+
+// integer fast path of the edge detector for 8-bit images: a 766 x 766 bit table per threshold
+int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s);
+size_t edge_lut_words();
+int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
+                     const uint32_t *lut, uint8_t *edges, cudaStream_t s);
 
 int launch_fill_web_holes_step(const int32_t *src, int32_t *dst, int W, int H, cudaStream_t s);
 int launch_minmax(const int32_t *a, size_t n, int32_t *d_minmax, cudaStream_t s);

@@ -51,10 +51,15 @@ struct sm_ctx {
     int img_kind = 0;  // 0 none, 1 u8, 2 f64
     uint8_t *edges[2] = {nullptr, nullptr};
     bool have_edges = false;
+    uint32_t *edge_lut = nullptr;  // detector decisions for all (L, R) sum pairs at lut_threshold
+    double lut_threshold = -1.0;
+    bool edges_fp64_only = false;  // SM_EDGES_FP64=1: always take the FP64 kernel (cross-check)
     int32_t *best = nullptr, *web = nullptr;
     bool have_web = false;
     int32_t *web2 = nullptr, *tmp = nullptr;  // step 3 ping-pong
+    const int32_t *web_filled = nullptr;      // result of fill_web_holes (may alias web)
     bool have_web2 = false;
+    bool web_may_have_holes = false;          // only a web from sm_set_web can contain zeros
     uint8_t *out = nullptr;
     bool have_out = false;
     int32_t *minmax = nullptr;
@@ -312,6 +317,7 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
     c->g.ER = c->g.BH + 2 * c->half;
     c->g.D = num_shifts;
     c->g.WPR = packed_words_per_row(width, c->half, num_shifts);
+    c->edges_fp64_only = getenv("SM_EDGES_FP64") && atoi(getenv("SM_EDGES_FP64")) != 0;
 
     int rc = SM_OK;
     auto fail = [&](int code) {
@@ -332,6 +338,19 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
         (rc = dev_alloc(&c->LA, pw)) || (rc = dev_alloc(&c->LB, pw)) || (rc = dev_alloc(&c->RB, pw)) ||
         (rc = dev_alloc(&c->minmax, 2)))
         return fail(rc);
+    // whole-frame contexts run step 3 as well: its buffers belong to the untimed set-up, like
+    // the allocations at the top of the reference's algorithm() (stereo.cu:299-306)
+    if (row0 == 0 && row1 == frame_height && ((rc = dev_alloc(&c->tmp, n)) || (rc = dev_alloc(&c->out, n))))
+        return fail(rc);
+    // load the kernels this geometry uses now, not inside the first timed call
+    warm_edges(variant);
+    warm_pack(variant);
+    warm_direct();
+    warm_step3();
+    if (bitslice_supports(c->half, c->D)) {
+        HotArgs a = hot_args(c, c->best, c->web);
+        if ((rc = prepare_bitslice(a, c->num_sms)) < 0) return fail(rc);
+    }
     *out = c;
     return SM_OK;
 }
@@ -348,6 +367,7 @@ extern "C" int sm_destroy(sm_ctx *c)
     DeviceGuard guard(c->device);
     if (c->shadow) sm_destroy(c->shadow);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->edge_lut) cudaFree(c->edge_lut);
     void *ptrs[] = {c->img_u8[0], c->img_u8[1], c->img_f64[0], c->img_f64[1], c->edges[0], c->edges[1],
                     c->best,      c->web,       c->web2,       c->tmp,        c->out,      c->minmax,
                     c->LA,        c->LB,        c->RB,         c->scratch_u8, c->scratch_i32};
@@ -460,12 +480,24 @@ extern "C" int sm_edges(sm_ctx *c, double threshold)
         ystart = 0;
         nrows = c->FH;
     }
+    const bool use_lut = c->img_kind == 1 && !c->edges_fp64_only;
+    if (use_lut && c->lut_threshold != threshold) {
+        int rc;
+        if ((rc = dev_alloc(&c->edge_lut, edge_lut_words()))) return rc;
+        if ((rc = launch_edge_lut(threshold, c->edge_lut, c->stream)) < 0) return rc;
+        c->lut_threshold = threshold;
+    }
     for (int k = 0; k < 2; k++) {
-        int rc = c->img_kind == 1
-                     ? launch_edges<uint8_t>(c->img_u8[k], c->W, c->FH, ystart, nrows, c->variant,
-                                             threshold, c->edges[k], c->stream)
-                     : launch_edges<double>(c->img_f64[k], c->W, c->FH, ystart, nrows, c->variant,
-                                            threshold, c->edges[k], c->stream);
+        int rc;
+        if (use_lut)
+            rc = launch_edges_lut(c->img_u8[k], c->W, c->FH, ystart, nrows, c->variant, threshold, c->edge_lut,
+                                  c->edges[k], c->stream);
+        else if (c->img_kind == 1)
+            rc = launch_edges<uint8_t>(c->img_u8[k], c->W, c->FH, ystart, nrows, c->variant, threshold,
+                                       c->edges[k], c->stream);
+        else
+            rc = launch_edges<double>(c->img_f64[k], c->W, c->FH, ystart, nrows, c->variant, threshold,
+                                      c->edges[k], c->stream);
         if (rc < 0) return rc;
     }
     c->have_edges = true;
@@ -496,6 +528,7 @@ extern "C" int sm_match_wta(sm_ctx *c)
     int rc = run_hot(c, c->edges[0], c->edges[1], c->best, c->web);
     if (rc) return rc;
     c->have_web = true;
+    c->web_may_have_holes = false;
     c->have_web2 = c->have_out = false;
     return SM_OK;
 }
@@ -640,6 +673,15 @@ extern "C" int sm_fill_web_holes(sm_ctx *c, int times)
     }
     SM_REQUIRE(times >= 0, "sm_fill_web_holes: times must be >= 0");
     SM_REQUIRE(c->row0 == 0 && c->row1 == c->FH, "sm_fill_web_holes: whole-frame contexts only");
+    if (!c->web_may_have_holes) {
+        // fill_web_holes only ever writes where the web is 0 (stereo.cu:238), and the web that
+        // sm_match_wta produces is >= 1 everywhere (some shift always equals the maximum,
+        // stereo.c:212-219): every one of the `times` passes is the identity, so
+        // the filled web IS the web.  No kernel, no copy.
+        c->web_filled = c->web;
+        c->have_web2 = true;
+        return SM_OK;
+    }
     int rc;
     size_t n = c->npix();
     if ((rc = dev_alloc(&c->web2, n)) || (rc = dev_alloc(&c->tmp, n))) return rc;
@@ -655,7 +697,23 @@ extern "C" int sm_fill_web_holes(sm_ctx *c, int times)
     }
     c->web2 = a;  // whichever buffer the reference would return as `web`
     c->tmp = b;
+    c->web_filled = c->web2;
     c->have_web2 = true;
+    return SM_OK;
+}
+
+// Step 3 on a caller-supplied web (host, i32): the only way a web with holes (zeros) can
+// enter the library; makes fill_web_holes / draw_contour_map usable and testable on their own.
+extern "C" int sm_set_web(sm_ctx *c, const int32_t *web)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(web, "sm_set_web: NULL web");
+    SM_REQUIRE(c->row0 == 0 && c->row1 == c->FH, "sm_set_web: whole-frame contexts only");
+    SM_CUDA(cudaMemcpyAsync(c->web, web, c->npix() * 4, cudaMemcpyHostToDevice, c->stream));
+    SM_CUDA(cudaMemsetAsync(c->best, 0, c->npix() * 4, c->stream));
+    c->have_web = true;
+    c->web_may_have_holes = true;
+    c->have_web2 = c->have_out = false;
     return SM_OK;
 }
 
@@ -667,7 +725,7 @@ extern "C" int sm_draw_contour_map(sm_ctx *c, int lines, int32_t *web_min, int32
         return SM_ERR_STATE;
     }
     SM_REQUIRE(c->row0 == 0 && c->row1 == c->FH, "sm_draw_contour_map: whole-frame contexts only");
-    const int32_t *web = c->have_web2 ? c->web2 : c->web;
+    const int32_t *web = c->have_web2 ? c->web_filled : c->web;
     int rc;
     if ((rc = dev_alloc(&c->out, c->npix()))) return rc;
     if ((rc = launch_minmax(web, c->npix(), c->minmax, c->stream)) < 0) return rc;
@@ -730,7 +788,7 @@ extern "C" int sm_download(sm_ctx *c, int which, int shift, void *host)
         break;
     case SM_WEB_FILLED:
         if (!c->have_web2) goto state;
-        rc = copy_band_d2h(c, (int32_t *)host, c->web2);
+        rc = copy_band_d2h(c, (int32_t *)host, c->web_filled);
         break;
     case SM_OUTPUT:
         if (!c->have_out) goto state;

@@ -194,6 +194,17 @@ def test_step3(orc):
             rc, out = orc.draw_contour_map(filled, 10)
             assert rc == 0 and np.array_equal(c.download(smb.OUTPUT), out)
             assert np.array_equal(c.download_web_u8(), web.astype(np.uint8))
+    # a web WITH holes (only reachable through sm_set_web) runs the real hole-filling kernels
+    rng = np.random.default_rng(9)
+    holes = web.copy()
+    holes[rng.random(web.shape) < 0.2] = 0
+    holes[0, :7] = 0
+    holes[-1, -5:] = 0
+    for times in (0, 1, 2, 7, 32):
+        with _ctx(w, h, 30, 21, smb.WRAP) as c:
+            c.set_web(holes)
+            c.fill_web_holes(times)
+            assert np.array_equal(c.download(smb.WEB_FILLED), orc.fill_web_holes(holes, times)), times
     # degenerate range: the reference divides by zero; the library reports it
     z = np.zeros((32, 32), np.uint8)
     with _ctx(32, 32, 8, 3, smb.WRAP) as c:
