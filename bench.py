@@ -224,7 +224,9 @@ def run_b200_arm(a, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # control plane only (barrier + max of the per-rank time): the data path has no exchange step,
+        # so no NCCL communicator is ever needed; gloo keeps stdout to the one JSON line
+        dist.init_process_group("gloo")
     variant = smb.GHOST if a.variant == "ghost" else smb.WRAP
     B, distinct = a.pairs, min(a.pairs, a.distinct)
 
@@ -295,7 +297,7 @@ def run_b200_arm(a, rank, world, local_rank):
     n_iso, pack_ms, main_ms = ctx.profile_read()
     ctx.profile_begin(0)
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     mde_step = B * W * H * D
@@ -318,7 +320,7 @@ def run_b200_arm(a, rank, world, local_rank):
     barrier()
     te = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([te], dtype=torch.float64, device=dev)
+        t = torch.tensor([te], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te = float(t.item())
     e2e_val = world * Be * W * H * D * e2e_steps / te / 1e6
