@@ -463,10 +463,13 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
     int slots = num_sms * blocks_per_sm;
     int segs = slots / strips;
     if (segs < 1) segs = 1;
-    int min_rows = 4 * C::N > 32 ? 4 * C::N : 32;
+    // a run is at least as long as its own warm-up (2*half rows) and one block
+    int min_rows = 2 * C::N > C::RB ? 2 * C::N : C::RB;
     int max_segs = (h.g.BH + min_rows - 1) / min_rows;
     if (segs > max_segs) segs = max_segs;
     a.rows_per_seg = (h.g.BH + segs - 1) / segs;
+    // whole blocks of RB rows per run: only the frame's last run has a ragged (slower, branchy) block
+    a.rows_per_seg = (a.rows_per_seg + C::RB - 1) / C::RB * C::RB;
     segs = (h.g.BH + a.rows_per_seg - 1) / a.rows_per_seg;
     dim3 grid(strips, segs);
     kern<<<grid, 32, C::SMEM, s>>>(a);
@@ -500,9 +503,17 @@ int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, bool 
 // square_width up to 21 (the reference default, stereo.c:8); wider windows take the direct kernel.
 bool bitslice_supports(int half, int D) { return half >= 0 && half <= 10 && D >= 1 && D <= 512; }
 
+// shift words per pass: 2 (64 shifts) unless 32 shifts cover D.  SMB_NW=1 forces one (experiment hook).
+static int words_per_pass(const HotArgs &h)
+{
+    static const int nw_env = getenv("SMB_NW") ? atoi(getenv("SMB_NW")) : 0;
+    if (h.g.D <= 32 || nw_env == 1) return 1;
+    return 2;
+}
+
 int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
 {
-    if (h.g.D <= 32) return dispatch_half<1>(h.g.half, h, num_sms, s, false);
+    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, s, false);
     return dispatch_half<2>(h.g.half, h, num_sms, s, false);
 }
 
@@ -510,7 +521,7 @@ int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
 // occupancy, so that the first sm_match_wta call pays none of that.
 int prepare_bitslice(const HotArgs &h, int num_sms)
 {
-    if (h.g.D <= 32) return dispatch_half<1>(h.g.half, h, num_sms, nullptr, true);
+    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, nullptr, true);
     return dispatch_half<2>(h.g.half, h, num_sms, nullptr, true);
 }
 
