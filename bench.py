@@ -288,7 +288,7 @@ def run_b200_arm(a, rank, world, local_rank):
     tw1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
     n_calls, _, overl_ms = ctx.profile_read()
-    launches = n_calls * 2  # one pack + one main kernel per pair
+    launches = a.steps * ctx.last_launches()  # per batch call: one pack + one main launch per group of pairs
     # the dominant kernel timed ALONE (one pair per call, nothing overlapped): the roofline figure
     niso = min(B, 32)
     ctx.profile_begin(niso)

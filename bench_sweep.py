@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from bench import THRESHOLD, synth_pair  # noqa: E402
 
 
-def measure(smb, orc, name, e1, e2, D, sw, variant, peak_gops, reps=12, check_rows=48):
+def measure(smb, orc, name, e1, e2, D, sw, variant, peak_gops, reps=12, check_rows=48, batch=0):
     h, w = e1.shape
     res = {}
     for kname, kernel in (("bitslice", smb.KERNEL_BITSLICE), ("direct", smb.KERNEL_DIRECT)):
@@ -69,6 +69,33 @@ def measure(smb, orc, name, e1, e2, D, sw, variant, peak_gops, reps=12, check_ro
            "roofline_frac_int_alu": round(8 * mde / t / (peak_gops * 1e9), 3),
            "direct_kernel_us": round(res["direct"]["main_us"], 1) if "direct" in res else None,
            "equal_direct_kernel": ok_direct, "equal_oracle_slab": ok_oracle}
+    if batch:
+        # device-resident batch of `batch` copies of the pair through sm_match_wta_dev_batch
+        import torch
+        d1 = torch.from_numpy(e1).cuda().unsqueeze(0).repeat(batch, 1, 1).contiguous()
+        d2 = torch.from_numpy(e2).cuda().unsqueeze(0).repeat(batch, 1, 1).contiguous()
+        bb = torch.empty((batch, h, w), dtype=torch.int32, device="cuda")
+        ww = torch.empty((batch, h, w), dtype=torch.int32, device="cuda")
+        with smb.StereoContext(w, h, D, sw, variant) as c:
+            st = torch.cuda.current_stream()
+            c.set_stream(st.cuda_stream)
+            run = lambda: c.match_wta_dev_batch(batch, d1.data_ptr(), d2.data_ptr(), h * w, bb.data_ptr(),
+                                                ww.data_ptr(), h * w)
+            for _ in range(3):
+                run()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record(st)
+            for _ in range(5):
+                run()
+            ev1.record(st)
+            torch.cuda.synchronize()
+            us = ev0.elapsed_time(ev1) * 1e3 / 5 / batch
+        out["batch_pairs"] = batch
+        out["batch_us_per_pair"] = round(us, 2)
+        out["batch_GMDE_per_s"] = round(mde / (us * 1e-6) / 1e9, 1)
+        out["batch_equal"] = bool(np.array_equal(ww[batch - 1].cpu().numpy(), b["web"]) and
+                                  np.array_equal(bb[0].cpu().numpy(), b["best"]))
     print(json.dumps(out), flush=True)
     return out
 
@@ -108,7 +135,12 @@ def main():
         left, right, _ = synth_pair(1234, 1280, 720, 128)
         for variant in (0, 1):
             e1, e2 = edges_of(left, right, 128, 21, variant)
-            rows.append(measure(smb, orc, "c4", e1, e2, 128, 21, variant, peak))
+            rows.append(measure(smb, orc, "c4", e1, e2, 128, 21, variant, peak, batch=64))
+    if "c2" in what:
+        left, right, _ = synth_pair(1234, 1920, 1080, 64)
+        for variant in (0, 1):
+            e1, e2 = edges_of(left, right, 64, 9, variant)
+            rows.append(measure(smb, orc, "c2", e1, e2, 64, 9, variant, peak, batch=64))
     if "sweep" in what:
         for D in (16, 32, 64, 128, 256, 512):
             left, right, _ = synth_pair(1234, 1920, 1080, D)

@@ -264,6 +264,12 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
     uint32_t *H5 = reinterpret_cast<uint32_t *>(Hq + NR * NW * HROW);  // [NR][NW][HROW] (KH == 5)
     uint32_t *Mq = H5 + C::H5N;                                        // [NRM][MROW], word (x, w) at x*NW + w
 
+    // one pair per grid z-slice
+    a.h.LA += blockIdx.z * a.h.plane_stride;
+    a.h.LB += blockIdx.z * a.h.plane_stride;
+    a.h.RB += blockIdx.z * a.h.plane_stride;
+    a.h.best += blockIdx.z * a.h.out_stride;
+    a.h.web += blockIdx.z * a.h.out_stride;
     const PackedGeom &g = a.h.g;
     const int lane = threadIdx.x;
     const int x0 = blockIdx.x * TW;
@@ -461,7 +467,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
     const int strips = (h.g.W + C::TW - 1) / C::TW;
     // aim at one full wave of resident warps; keep runs long enough to amortise the 2*half warm-up rows
     int slots = num_sms * blocks_per_sm;
-    int segs = slots / strips;
+    int segs = slots / (strips * h.npairs);
     if (segs < 1) segs = 1;
     // a run is at least as long as its own warm-up (2*half rows) and one block
     int min_rows = 2 * C::N > C::RB ? 2 * C::N : C::RB;
@@ -471,7 +477,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
     // whole blocks of RB rows per run: only the frame's last run has a ragged (slower, branchy) block
     a.rows_per_seg = (a.rows_per_seg + C::RB - 1) / C::RB * C::RB;
     segs = (h.g.BH + a.rows_per_seg - 1) / a.rows_per_seg;
-    dim3 grid(strips, segs);
+    dim3 grid(strips, segs, h.npairs);
     kern<<<grid, 32, C::SMEM, s>>>(a);
     SM_CUDA(cudaGetLastError());
     return 1;
@@ -479,7 +485,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
 
 // walker segment length per window size: shorter walks = less shared memory (fewer rows
 // per block) but more warm-up steps per output
-constexpr int seg_for(int half, int nw) { return nw == 1 ? 16 : (half <= 5 ? 16 : 32); }
+constexpr int seg_for(int half, int nw) { return 16; }
 
 template <int NW>
 int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
@@ -488,6 +494,7 @@ int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, bool 
     static const int seg_env = getenv("SMB_SEG") ? atoi(getenv("SMB_SEG")) : 0;
     if (half == 4 && NW == 2 && seg_env == 8) return launch_one<4, 2, 8>(h, num_sms, s, prepare_only);
     if (half == 4 && NW == 2 && seg_env == 32) return launch_one<4, 2, 32>(h, num_sms, s, prepare_only);
+    if (half == 10 && NW == 2 && seg_env == 32) return launch_one<10, 2, 32>(h, num_sms, s, prepare_only);
     switch (half) {
 #define SM_CASE(HF) \
     case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s, prepare_only);
@@ -515,6 +522,26 @@ int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
 {
     if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, s, false);
     return dispatch_half<2>(h.g.half, h, num_sms, s, false);
+}
+
+// How many pairs of a batch to put into one launch.  Every warp pays 2*half warm-up rows per
+// run, so runs should be as long as the frame allows: pairs are added to the launch until one
+// warp per strip walks the whole height (measured on config 2: 24 us per pair with one pair
+// per launch, 18.3 us with 12 or more).
+int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
+{
+    const int N = 2 * h.g.half + 1, strips = (h.g.W + 31) / 32;
+    const int slots = num_sms * 8;  // typical residency; only a sizing heuristic
+    static const int want_env = getenv("SMB_WANT") ? atoi(getenv("SMB_WANT")) : 1000;  // in windows; experiment hook
+    const int want_rows = h.g.BH < want_env * N ? h.g.BH : want_env * N;
+    int p = 1;
+    while (p < max_pairs) {
+        int segs = slots / (strips * p);
+        if (segs < 1) segs = 1;
+        if ((h.g.BH + segs - 1) / segs >= want_rows) break;
+        p++;
+    }
+    return p;
 }
 
 // Loads the kernel this geometry will use, sets its shared-memory attribute and caches its

@@ -29,8 +29,14 @@ __device__ __forceinline__ uint32_t gather32(const uint4 &a, const uint4 &b)
 template <int VARIANT>
 __global__ void __launch_bounds__(128)
 k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, int row0,
-       PackedGeom g, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB, uint32_t *__restrict__ RB)
+       PackedGeom g, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB, uint32_t *__restrict__ RB,
+       size_t edge_stride, size_t plane_stride)
 {
+    e1 += blockIdx.z * edge_stride;  // one pair per grid z-slice
+    e2 += blockIdx.z * edge_stride;
+    LA += blockIdx.z * plane_stride;
+    LB += blockIdx.z * plane_stride;
+    RB += blockIdx.z * plane_stride;
     const int wd = blockIdx.x * blockDim.x + threadIdx.x;  // lane <-> word, a warp covers 32 words
     const int lane = threadIdx.x & 31;
     const int pr = blockIdx.y;
@@ -89,14 +95,15 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
 }
 
 int launch_pack(const uint8_t *e1, const uint8_t *e2, int FH, int row0, int variant,
-                const PackedGeom &g, uint32_t *LA, uint32_t *LB, uint32_t *RB, cudaStream_t s)
+                const PackedGeom &g, uint32_t *LA, uint32_t *LB, uint32_t *RB, cudaStream_t s,
+                int npairs, size_t edge_stride, size_t plane_stride)
 {
     dim3 block(128);
-    dim3 grid((g.WPR + block.x - 1) / block.x, g.ER);
+    dim3 grid((g.WPR + block.x - 1) / block.x, g.ER, npairs);
     if (variant == SM_WRAP)
-        k_pack<SM_WRAP><<<grid, block, 0, s>>>(e1, e2, FH, row0, g, LA, LB, RB);
+        k_pack<SM_WRAP><<<grid, block, 0, s>>>(e1, e2, FH, row0, g, LA, LB, RB, edge_stride, plane_stride);
     else
-        k_pack<SM_GHOST><<<grid, block, 0, s>>>(e1, e2, FH, row0, g, LA, LB, RB);
+        k_pack<SM_GHOST><<<grid, block, 0, s>>>(e1, e2, FH, row0, g, LA, LB, RB, edge_stride, plane_stride);
     SM_CUDA(cudaGetLastError());
     return 1;
 }

@@ -71,15 +71,21 @@ struct HotArgs {
     const uint32_t *LA, *LB, *RB;  // [ER][WPR]
     int32_t *best, *web;           // frame arrays [FH][W]; band row j -> frame row row0 + j
     int row0;
+    // several independent pairs in one launch (blockIdx.z): pair p's planes are plane_stride
+    // words further, its outputs out_stride elements further
+    int npairs = 1;
+    size_t plane_stride = 0, out_stride = 0;
 };
 
 // launchers (each returns the number of kernels launched, or a negative sm_status)
 int launch_pack(const uint8_t *e1, const uint8_t *e2, int FH, int row0, int variant,
-                const PackedGeom &g, uint32_t *LA, uint32_t *LB, uint32_t *RB, cudaStream_t s);
+                const PackedGeom &g, uint32_t *LA, uint32_t *LB, uint32_t *RB, cudaStream_t s,
+                int npairs = 1, size_t edge_stride = 0, size_t plane_stride = 0);
 int launch_direct(const HotArgs &a, cudaStream_t s);
 int launch_bitslice(const HotArgs &a, int num_sms, cudaStream_t s);
 bool bitslice_supports(int half, int D);
 int prepare_bitslice(const HotArgs &a, int num_sms);
+int bitslice_pairs_per_launch(const HotArgs &a, int num_sms, int max_pairs);
 // force the (lazily loaded) kernels of each translation unit into the context
 void warm_edges(int variant);
 void warm_pack(int variant);

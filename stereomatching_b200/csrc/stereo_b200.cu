@@ -70,6 +70,7 @@ struct sm_ctx {
     static constexpr int NPB = 3;
     cudaStream_t pack_stream = nullptr, main2_stream = nullptr;  // main kernels alternate stream / main2_stream
     cudaEvent_t ev_join = nullptr;
+    int batch_group = 1;  // pairs per launch in sm_match_wta_dev_batch
     uint32_t *pLA[NPB] = {nullptr, nullptr, nullptr}, *pLB[NPB] = {nullptr, nullptr, nullptr},
              *pRB[NPB] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_packed[NPB] = {nullptr, nullptr, nullptr}, ev_used[NPB] = {nullptr, nullptr, nullptr};
@@ -550,38 +551,51 @@ extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_f
                "sm_match_wta_dev_batch: bad arguments");
     SM_REQUIRE(edge_stride >= c->npix() && out_stride >= c->npix(), "sm_match_wta_dev_batch: stride below frame size");
     constexpr int NPB = sm_ctx::NPB;
+    const size_t pw = (size_t)c->g.ER * c->g.WPR;
     if (!c->pack_stream) {
+        // pairs per launch: enough that every warp's run of rows is long against its warm-up rows
+        int kk = c->kernel;
+        if (kk == SM_KERNEL_AUTO) kk = bitslice_supports(c->half, c->D) ? SM_KERNEL_BITSLICE : SM_KERNEL_DIRECT;
+        c->batch_group = 1;
+        if (kk == SM_KERNEL_BITSLICE) {
+            HotArgs a = hot_args(c, d_best, d_web);
+            const int pmax = getenv("SMB_PMAX") ? atoi(getenv("SMB_PMAX")) : 16;  // experiment hook
+            c->batch_group = bitslice_pairs_per_launch(a, c->num_sms, pmax);
+        }
         SM_CUDA(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
         SM_CUDA(cudaStreamCreateWithFlags(&c->main2_stream, cudaStreamNonBlocking));
         SM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         SM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-        const size_t pw = (size_t)c->g.ER * c->g.WPR;
         for (int k = 0; k < NPB; k++) {
             int rc;
-            if ((rc = dev_alloc(&c->pLA[k], pw)) || (rc = dev_alloc(&c->pLB[k], pw)) || (rc = dev_alloc(&c->pRB[k], pw)))
+            if ((rc = dev_alloc(&c->pLA[k], pw * c->batch_group)) || (rc = dev_alloc(&c->pLB[k], pw * c->batch_group)) ||
+                (rc = dev_alloc(&c->pRB[k], pw * c->batch_group)))
                 return rc;
             SM_CUDA(cudaEventCreateWithFlags(&c->ev_packed[k], cudaEventDisableTiming));
             SM_CUDA(cudaEventCreateWithFlags(&c->ev_used[k], cudaEventDisableTiming));
         }
     }
+    const int G = c->batch_group;
     // everything queued on the context's stream so far (the producers of the edge maps) comes first
     SM_CUDA(cudaEventRecord(c->ev0, c->stream));
     SM_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     SM_CUDA(cudaStreamWaitEvent(c->pack_stream, c->ev_fork, 0));
     SM_CUDA(cudaStreamWaitEvent(c->main2_stream, c->ev_fork, 0));
-    int launches = 0;
-    for (int k = 0; k < n_pairs; k++) {
-        const int b = k % NPB;
+    int launches = 0, group = 0;
+    for (int k = 0; k < n_pairs; k += G, group++) {
+        const int np = n_pairs - k < G ? n_pairs - k : G;  // pairs in this launch
+        const int b = group % NPB;
         int rc;
-        if (k >= NPB) SM_CUDA(cudaStreamWaitEvent(c->pack_stream, c->ev_used[b], 0));  // main(k - NPB) is done with set b
+        if (group >= NPB) SM_CUDA(cudaStreamWaitEvent(c->pack_stream, c->ev_used[b], 0));  // set b is free again
         rc = launch_pack(d_first_edges + (size_t)k * edge_stride, d_second_edges + (size_t)k * edge_stride, c->FH,
-                         c->row0, c->variant, c->g, c->pLA[b], c->pLB[b], c->pRB[b], c->pack_stream);
+                         c->row0, c->variant, c->g, c->pLA[b], c->pLB[b], c->pRB[b], c->pack_stream, np,
+                         edge_stride, pw);
         if (rc < 0) return rc;
         launches += rc;
         SM_CUDA(cudaEventRecord(c->ev_packed[b], c->pack_stream));
-        // consecutive pairs are independent: alternate two streams so that the next main
-        // kernel's CTAs fill the SM slots the previous one frees (no tail / ramp between pairs)
-        cudaStream_t ms = (k & 1) ? c->main2_stream : c->stream;
+        // consecutive launches are independent: alternate two streams so that the next main
+        // kernel's warps fill the SM slots the previous one frees (no tail / ramp between them)
+        cudaStream_t ms = (group & 1) ? c->main2_stream : c->stream;
         SM_CUDA(cudaStreamWaitEvent(ms, c->ev_packed[b], 0));
         cudaEvent_t *pe = (c->prof_ev && c->prof_n < c->prof_cap) ? c->prof_ev + 3 * c->prof_n : nullptr;
         if (pe) {
@@ -592,6 +606,9 @@ extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_f
         a.LA = c->pLA[b];
         a.LB = c->pLB[b];
         a.RB = c->pRB[b];
+        a.npairs = np;
+        a.plane_stride = pw;
+        a.out_stride = out_stride;
         rc = launch_main(c, a, ms);
         if (rc < 0) return rc;
         launches += rc;
