@@ -405,6 +405,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if local_rank == 0:
+        import __graft_entry__
+        __graft_entry__.ensure_built()  # compile step only; there is no fallback path
     if a.impl == "reference":
         run_reference_arm(a, rank)
     else:
