@@ -135,7 +135,7 @@ def main():
         left, right, _ = synth_pair(1234, 1280, 720, 128)
         for variant in (0, 1):
             e1, e2 = edges_of(left, right, 128, 21, variant)
-            rows.append(measure(smb, orc, "c4", e1, e2, 128, 21, variant, peak, batch=64))
+            rows.append(measure(smb, orc, "c4", e1, e2, 128, 21, variant, peak, batch=256))
     if "c2" in what:
         left, right, _ = synth_pair(1234, 1920, 1080, 64)
         for variant in (0, 1):

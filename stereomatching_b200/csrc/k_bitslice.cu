@@ -465,13 +465,22 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
     BitsliceArgs a;
     a.h = h;
     const int strips = (h.g.W + C::TW - 1) / C::TW;
-    // aim at one full wave of resident warps; keep runs long enough to amortise the 2*half warm-up rows
-    int slots = num_sms * blocks_per_sm;
-    int segs = slots / (strips * h.npairs);
-    if (segs < 1) segs = 1;
     // a run is at least as long as its own warm-up (2*half rows) and one block
-    int min_rows = 2 * C::N > C::RB ? 2 * C::N : C::RB;
-    int max_segs = (h.g.BH + min_rows - 1) / min_rows;
+    const int min_rows = 2 * C::N > C::RB ? 2 * C::N : C::RB;
+    int segs;
+    if (h.npairs == 1) {
+        // latency mode (one pair): one full wave of resident warps
+        segs = num_sms * blocks_per_sm / strips;
+    } else {
+        // throughput mode (several pairs per launch): runs of about SMB_TR windows, whatever the
+        // number of CTAs -- the launch may be several waves deep, the block scheduler keeps the
+        // slots full and the next launch (other stream) covers the tail
+        static const int tr_env = getenv("SMB_TR") ? atoi(getenv("SMB_TR")) : 32;  // experiment hook
+        const int want = tr_env * C::N;
+        segs = (h.g.BH + want - 1) / want;
+    }
+    if (segs < 1) segs = 1;
+    const int max_segs = (h.g.BH + min_rows - 1) / min_rows;
     if (segs > max_segs) segs = max_segs;
     a.rows_per_seg = (h.g.BH + segs - 1) / segs;
     // whole blocks of RB rows per run: only the frame's last run has a ragged (slower, branchy) block
@@ -530,17 +539,13 @@ int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
 // per launch, 18.3 us with 12 or more).
 int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 {
+    // enough pairs that one launch is a few waves of warps (about 8 resident per SM)
     const int N = 2 * h.g.half + 1, strips = (h.g.W + 31) / 32;
-    const int slots = num_sms * 8;  // typical residency; only a sizing heuristic
-    static const int want_env = getenv("SMB_WANT") ? atoi(getenv("SMB_WANT")) : 1000;  // in windows; experiment hook
-    const int want_rows = h.g.BH < want_env * N ? h.g.BH : want_env * N;
+    static const int tr_env = getenv("SMB_TR") ? atoi(getenv("SMB_TR")) : 32;
+    const int want = tr_env * N;
+    const int segs = (h.g.BH + want - 1) / want > 0 ? (h.g.BH + want - 1) / want : 1;
     int p = 1;
-    while (p < max_pairs) {
-        int segs = slots / (strips * p);
-        if (segs < 1) segs = 1;
-        if ((h.g.BH + segs - 1) / segs >= want_rows) break;
-        p++;
-    }
+    while (p < max_pairs && strips * segs * p < 3 * num_sms * 8) p++;
     return p;
 }
 
