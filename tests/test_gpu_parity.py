@@ -312,6 +312,29 @@ def test_device_batch_entry_overlapped_pack(orc):
             assert np.array_equal(best[k].cpu().numpy(), bo) and np.array_equal(web[k].cpu().numpy(), wo), k
 
 
+def test_device_batch_many_small_pairs(orc):
+    """More pairs than one launch holds (16) and than the rotating plane sets (3 x 16): 53 pairs,
+    the last launch ragged; direct kernel too (one pair per launch)."""
+    torch = pytest.importorskip("torch")
+    n, w, h, D, sw = 53, 96, 40, 40, 7
+    rng = np.random.default_rng(11)
+    e1 = (rng.random((n, h, w)) < 0.3).astype(np.uint8)
+    e2 = np.stack([np.roll(e1[k], k % D, axis=1) for k in range(n)])
+    expect = [orc.match_wta(e1[k], e2[k], D, sw, smb.GHOST) for k in range(n)]
+    d1, d2 = torch.from_numpy(e1).cuda(), torch.from_numpy(e2).cuda()
+    for kernel in KERNELS:
+        best = torch.full((n, h, w), -7, dtype=torch.int32, device="cuda")
+        web = torch.full((n, h, w), -7, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        with _ctx(w, h, D, sw, smb.GHOST, kernel) as c:
+            c.set_stream(torch.cuda.current_stream().cuda_stream)
+            c.match_wta_dev_batch(n, d1.data_ptr(), d2.data_ptr(), h * w, best.data_ptr(), web.data_ptr(), h * w)
+            torch.cuda.synchronize()
+        for k in range(n):
+            assert np.array_equal(best[k].cpu().numpy(), expect[k][0]), (kernel, k)
+            assert np.array_equal(web[k].cpu().numpy(), expect[k][1]), (kernel, k)
+
+
 # ---------------------------------------------------------------------------------
 # full-size properties (sizes the CPU oracle cannot finish in seconds)
 # ---------------------------------------------------------------------------------
