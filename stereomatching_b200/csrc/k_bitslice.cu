@@ -317,23 +317,26 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
         WalkRaw in = {};
         if (ja + wr < last_pr) load_walk_raw(in, a.h, ja + wr, rbit, lbit);
         int slot0 = 0, mslot0 = 0;  // ring slots of padded row p0
-        int32_t *pbest = a.h.best + (size_t)(a.h.row0 + ja) * g.W + ximg;  // next output row
-        int32_t *pweb = a.h.web + (size_t)(a.h.row0 + ja) * g.W + ximg;
+        // next output row, as a 32-bit element offset (frames are < 2^31 pixels): the address
+        // arithmetic then is one multiply-add per store (FMA pipe) instead of 64-bit pointer adds
+        int oidx = (a.h.row0 + ja) * g.W + ximg;
 
         // store NR_ finished rows (best, idx) and advance the output pointers
         auto put = [&](int best, int idx) {
             const int web = 32 * wg0 + idx + 1;
             bool st = store_ok;
-            if (MULTI && chunk != 0 && st) st = best >= *pbest;  // a later chunk wins ties (higher shifts)
-            store_if(pbest, best, st);
-            store_if(pweb, web, st);
-            pbest += g.W;
-            pweb += g.W;
+            if (MULTI && chunk != 0 && st) st = best >= a.h.best[oidx];  // a later chunk wins ties (higher shifts)
+            store_if(a.h.best + oidx, best, st);
+            store_if(a.h.web + oidx, web, st);
+            oidx += g.W;
         };
         auto load_m = [&](int mslot_c, uint32_t (&M)[NW]) {
 #pragma unroll
             for (int w = 0; w < NW; w++) M[w] = Mq[mslot_c * MROW + lane * NW + w];
         };
+        // ring index helpers: x in [0, 2n) -> x mod n, and x in [-n, n) -> x mod n, as one add + one unsigned min
+        auto wrap_hi = [](int x, int n) { return (int)min((unsigned)x, (unsigned)(x - n)); };
+        auto wrap_lo = [](int x, int n) { return (int)min((unsigned)x, (unsigned)(x + n)); };
         auto wrap_m = [&](int ms) { return ms < 0 ? ms + NRM : (ms >= NRM ? ms - NRM : ms); };
 
         for (int p0 = ja; p0 < last_pr; p0 += RB) {
@@ -378,10 +381,8 @@ __global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
                     uint32_t Vs[G][NW][PV], Ms[G][NW];
 #pragma unroll
                     for (int k = 0; k < G; k++) {
-                        int slot_n = slot0 + r + k;
-                        slot_n = slot_n >= NR ? slot_n - NR : slot_n;
-                        int slot_o = slot_n - N;
-                        slot_o = slot_o < 0 ? slot_o + NR : slot_o;
+                        const int slot_n = wrap_hi(slot0 + r + k, NR);
+                        const int slot_o = wrap_lo(slot_n - N, NR);
 #pragma unroll
                         for (int w = 0; w < NW; w++) {
                             uint32_t hn[5], ho[5];
@@ -492,18 +493,14 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
     return 1;
 }
 
-// walker segment length per window size: shorter walks = less shared memory (fewer rows
-// per block) but more warm-up steps per output
+// walker segment length: shorter walks = less shared memory (fewer rows per block) but more
+// warm-up steps per output.  Measured on config 2 (us per pair, batched): 8 -> 18.2, 16 -> 18.0,
+// 32 -> 25.2; on config 4: 16 -> 56, 32 -> 61.
 constexpr int seg_for(int half, int nw) { return 16; }
 
 template <int NW>
 int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
 {
-    // experiment hook: SMB_SEG=8|16|32 overrides the walker segment for half == 4
-    static const int seg_env = getenv("SMB_SEG") ? atoi(getenv("SMB_SEG")) : 0;
-    if (half == 4 && NW == 2 && seg_env == 8) return launch_one<4, 2, 8>(h, num_sms, s, prepare_only);
-    if (half == 4 && NW == 2 && seg_env == 32) return launch_one<4, 2, 32>(h, num_sms, s, prepare_only);
-    if (half == 10 && NW == 2 && seg_env == 32) return launch_one<10, 2, 32>(h, num_sms, s, prepare_only);
     switch (half) {
 #define SM_CASE(HF) \
     case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s, prepare_only);
@@ -519,13 +516,9 @@ int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, bool 
 // square_width up to 21 (the reference default, stereo.c:8); wider windows take the direct kernel.
 bool bitslice_supports(int half, int D) { return half >= 0 && half <= 10 && D >= 1 && D <= 512; }
 
-// shift words per pass: 2 (64 shifts) unless 32 shifts cover D.  SMB_NW=1 forces one (experiment hook).
-static int words_per_pass(const HotArgs &h)
-{
-    static const int nw_env = getenv("SMB_NW") ? atoi(getenv("SMB_NW")) : 0;
-    if (h.g.D <= 32 || nw_env == 1) return 1;
-    return 2;
-}
+// shift words per pass: 2 (64 shifts) unless 32 shifts cover D (one word per pass with more
+// passes was measured slower: 87 vs 60 us on config 4)
+static int words_per_pass(const HotArgs &h) { return h.g.D <= 32 ? 1 : 2; }
 
 int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
 {
