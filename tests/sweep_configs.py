@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench_sweep.py -- the other BASELINE.json configs on one B200: kernel time, MDE/s and
+"""tests/sweep_configs.py -- parity + timing sweep over the other BASELINE.json configs on one B200: kernel time, MDE/s and
 roofline fraction of the hot path for
 
   c1     the five real fixtures (reference defaults: 30 shifts, window 21), both variants
@@ -10,7 +10,8 @@ roofline fraction of the hot path for
 For every point the bit-sliced kernel's result is compared bit for bit with the direct
 (literal window sum) kernel on the device, and with the CPU oracle on a horizontal slab.
 Writes one JSON line per point to stdout; --md also writes a markdown table.
-The oracle is used here only as the checker.
+Lives under tests/ because it uses the CPU oracle (as the checker only); run it by hand:
+    python tests/sweep_configs.py --what c1,c2,c3,c4,sweep --md out.md
 """
 import argparse
 import json
@@ -19,7 +20,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
