@@ -466,8 +466,9 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
     BitsliceArgs a;
     a.h = h;
     const int strips = (h.g.W + C::TW - 1) / C::TW;
-    // a run is at least as long as its own warm-up (2*half rows) and one block
-    const int min_rows = 2 * C::N > C::RB ? 2 * C::N : C::RB;
+    // a run is at least one block of rows.  (Short runs pay 2*half warm-up rows each, but they
+    // only happen when the frame is too small to fill the machine, where latency is what counts.)
+    const int min_rows = C::RB;
     int segs;
     if (h.npairs == 1) {
         // latency mode (one pair): one full wave of resident warps
