@@ -218,22 +218,22 @@ __device__ __forceinline__ void wta(const uint32_t (&V)[NR_][NW][PV], const uint
     for (int p = PV - 1; p >= 0; p--) {
 #pragma unroll
         for (int k = 0; k < NR_; k++) {
-            uint32_t t[NW], any = 0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                t[w] = lop3<0x80>(cand[k][w], V[k][w][p], M[k][w]);
-                any |= t[w];
-            }
+            // t = cand & V_p & M with the "any lane left" test folded into the same LOP3s: the
+            // predicate output of one feeds the next (lop3.or d|p), so a plane costs NW ALU
+            // instructions instead of NW + 1 (a separate OR-and-test)
             if (NW == 2) {
-                asm("{ .reg .pred q; setp.ne.u32 q, %3, 0;\n\t"
-                    "@q mad.lo.u32 %0, %4, %6, 0;\n\t@q mad.lo.u32 %1, %5, %6, 0;\n\t@q mad.lo.s32 %2, %6, %7, %2; }"
+                asm("{ .reg .pred q0, q; .reg .b32 t0, t1;\n\t"
+                    "lop3.or.b32 t0|q0, %0, %3, %4, 0x80, 0;\n\t"
+                    "lop3.or.b32 t1|q, %1, %5, %6, 0x80, q0;\n\t"
+                    "@q mad.lo.u32 %0, t0, %7, 0;\n\t@q mad.lo.u32 %1, t1, %7, 0;\n\t@q mad.lo.s32 %2, %7, %8, %2; }"
                     : "+r"(cand[k][0]), "+r"(cand[k][NW - 1]), "+r"(best[k])
-                    : "r"(any), "r"(t[0]), "r"(t[NW - 1]), "r"(one), "r"(1 << p));
+                    : "r"(V[k][0][p]), "r"(M[k][0]), "r"(V[k][NW - 1][p]), "r"(M[k][NW - 1]), "r"(one), "r"(1 << p));
             } else {
-                asm("{ .reg .pred q; setp.ne.u32 q, %2, 0;\n\t"
-                    "@q mad.lo.u32 %0, %3, %4, 0;\n\t@q mad.lo.s32 %1, %4, %5, %1; }"
+                asm("{ .reg .pred q; .reg .b32 t0;\n\t"
+                    "lop3.or.b32 t0|q, %0, %2, %3, 0x80, 0;\n\t"
+                    "@q mad.lo.u32 %0, t0, %4, 0;\n\t@q mad.lo.s32 %1, %4, %5, %1; }"
                     : "+r"(cand[k][0]), "+r"(best[k])
-                    : "r"(any), "r"(t[0]), "r"(one), "r"(1 << p));
+                    : "r"(V[k][0][p]), "r"(M[k][0]), "r"(one), "r"(1 << p));
             }
         }
     }
