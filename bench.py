@@ -12,7 +12,8 @@ working set is far larger than L2.
 
   value    whole-job MDE/s (pixels x shifts per second), device-timed, inputs resident
   e2e      the same metric through the C ABI with HOST buffers: sm_run_batch
-           (H2D u8 images -> edges -> hot path -> D2H i32 web) per step, wall clock
+           (H2D u8 images -> edges -> hot path -> D2H i32 web, a three-stage pipeline over groups
+           of pairs) per step, wall clock; e2e.link is the measured PCIe ceiling of that call
   roofline the main kernel against the INT32 issue rate measured on this GPU
            (the path is integer-ALU bound; HBM fraction reported alongside)
   cpu_baseline  the reference's own stereo.c hot path (oracle/_ref) on one host core
@@ -340,6 +341,8 @@ def run_b200_arm(a, rank, world, local_rank):
         te8 = float(t.item())
     e2e8_val = world * Be * W * H * D * e2e_steps / te8 / 1e6
     e2e8_ok = bool(np.array_equal(hweb8.array[0], hweb.array[0].astype(np.uint8)))
+    # the link's own ceiling for those two calls: pinned host<->device copies, both directions at once
+    h2d_gbs, d2h_gbs = smb.measure_copy_peak(local_rank, 2)
     # clocks: every sample taken between the start of the device-timed region and the end of the e2e one
     clocks = sampler.stop(tw0, time.perf_counter()) if sampler else None
 
@@ -395,6 +398,14 @@ def run_b200_arm(a, rank, world, local_rank):
                     "api": "sm_run_batch: pinned host u8 images -> H2D -> edges -> hot path -> D2H i32 web",
                     "timer": "host wall clock around synchronised API calls", "matches_resident_result": e2e_ok,
                     "frames_per_s": e2e_val * 1e6 / (W * H * D),
+                    "link": {"h2d_GBps": h2d_gbs, "d2h_GBps": d2h_gbs,
+                             "how": "sm_measure_copy_peak: 256 MB pinned copies, both directions at once, best of 3",
+                             "ceiling_MDE_per_s": world * W * H * D / max(2 * W * H / (h2d_gbs * 1e9),
+                                                                          4 * W * H / (d2h_gbs * 1e9)) / 1e6,
+                             "ceiling_with_u8_web_MDE_per_s": world * W * H * D / max(2 * W * H / (h2d_gbs * 1e9),
+                                                                                      W * H / (d2h_gbs * 1e9)) / 1e6,
+                             "note": "per pair 2 u8 images go up and one i32 (or u8) web comes down; the slower "
+                                     "direction bounds pairs/s, compute overlaps"},
                     "with_u8_web": {"value": e2e8_val, "unit": "MDE/s", "d2h_bytes_per_step": Be * W * H,
                                     "equal_to_i32_web": e2e8_ok,
                                     "note": "sm_run_batch(web_u8=1): same values, one byte per pixel"}},
@@ -414,7 +425,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=256, help="stereo pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs generated per GPU")
-    ap.add_argument("--e2e-pairs", type=int, default=64)
+    ap.add_argument("--e2e-pairs", type=int, default=128)
     ap.add_argument("--variant", default="wrap", choices=["wrap", "ghost"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 direct, 2 bit-sliced")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

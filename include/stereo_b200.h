@@ -181,6 +181,10 @@ int sm_profile_read(sm_ctx *ctx, int *n_calls, double *pack_ms_total, double *ma
  * MEASURED_PEAKS.json does not carry): mode 0 IADD3, 1 LOP3, 2 IADD3+IMAD, 3 LOP3+IMAD.
  * Result in 1e9 thread-instructions per second. */
 int sm_measure_int_peak(int device, int mode, double *gops_per_s);
+/* Pinned host <-> device copy bandwidth of the GPU's link, the ceiling of every figure
+ * measured with host buffers (sm_run_batch): mode 0 H2D alone, 1 D2H alone, 2 both
+ * directions at once.  gbs[0] = H2D GB/s, gbs[1] = D2H GB/s (0 for a direction not run). */
+int sm_measure_copy_peak(int device, int mode, double *gbs);
 
 /* ---- step 3 --------------------------------------------------- */
 

@@ -28,7 +28,7 @@ SYMBOLS = [
     "sm_create", "sm_create_band", "sm_destroy", "sm_set_stream", "sm_set_kernel",
     "sm_synchronize", "sm_upload_f64", "sm_upload_u8", "sm_edges", "sm_set_edges",
     "sm_match_wta", "sm_match_wta_dev", "sm_match_wta_dev_batch", "sm_elapsed_ms", "sm_last_launches",
-    "sm_profile_begin", "sm_profile_read", "sm_measure_int_peak",
+    "sm_profile_begin", "sm_profile_read", "sm_measure_int_peak", "sm_measure_copy_peak",
     "sm_fill_web_holes", "sm_set_web", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
     "sm_run_batch", "sm_band_rows",
 ]
@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         L.sm_profile_begin.argtypes = [vp, i]
         L.sm_profile_read.argtypes = [vp, C.POINTER(i), C.POINTER(d), C.POINTER(d)]
         L.sm_measure_int_peak.argtypes = [i, i, C.POINTER(d)]
+        L.sm_measure_copy_peak.argtypes = [i, i, C.POINTER(d)]
         L.sm_fill_web_holes.argtypes = [vp, i]
         L.sm_set_web.argtypes = [vp, vp]
         L.sm_draw_contour_map.argtypes = [vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -98,6 +99,13 @@ def measure_int_peak(device: int = 0, mode: int = 2) -> float:
     g = C.c_double()
     _check(lib().sm_measure_int_peak(device, mode, C.byref(g)))
     return g.value
+
+
+def measure_copy_peak(device: int = 0, mode: int = 2):
+    """Pinned host<->device copy bandwidth in GB/s as (h2d, d2h); mode 0 H2D alone, 1 D2H alone, 2 both at once."""
+    g = (C.c_double * 2)()
+    _check(lib().sm_measure_copy_peak(device, mode, g))
+    return g[0], g[1]
 
 
 def band_rows(height: int, n_bands: int, band: int):

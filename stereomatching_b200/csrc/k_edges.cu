@@ -175,8 +175,11 @@ __device__ __forceinline__ int edge_pixel(const uint8_t *__restrict__ img, int W
 template <int VARIANT>
 __global__ void __launch_bounds__(256)
 k_edges_lut(const uint8_t *__restrict__ img, int W, int FH, int ystart, int nrows, double thr,
-            const uint32_t *__restrict__ lut, uint8_t *__restrict__ edges)
+            const uint32_t *__restrict__ lut, uint8_t *__restrict__ edges, size_t image_stride)
 {
+    // one image per grid z-slice (sm_run_batch detects a whole group of images in one launch)
+    img += blockIdx.z * image_stride;
+    edges += blockIdx.z * image_stride;
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int r = blockIdx.y * blockDim.y + threadIdx.y;
     if (x4 >= W || r >= nrows) return;
@@ -233,14 +236,14 @@ int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s)
 size_t edge_lut_words() { return (size_t)LUT_N * LUT_WORDS; }
 
 int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
-                     const uint32_t *lut, uint8_t *edges, cudaStream_t s)
+                     const uint32_t *lut, uint8_t *edges, cudaStream_t s, int n_images, size_t image_stride)
 {
     dim3 block(64, 4);
-    dim3 grid(((W + 3) / 4 + block.x - 1) / block.x, (nrows + block.y - 1) / block.y);
+    dim3 grid(((W + 3) / 4 + block.x - 1) / block.x, (nrows + block.y - 1) / block.y, n_images);
     if (variant == SM_WRAP)
-        k_edges_lut<SM_WRAP><<<grid, block, 0, s>>>(img, W, FH, ystart, nrows, threshold, lut, edges);
+        k_edges_lut<SM_WRAP><<<grid, block, 0, s>>>(img, W, FH, ystart, nrows, threshold, lut, edges, image_stride);
     else
-        k_edges_lut<SM_GHOST><<<grid, block, 0, s>>>(img, W, FH, ystart, nrows, threshold, lut, edges);
+        k_edges_lut<SM_GHOST><<<grid, block, 0, s>>>(img, W, FH, ystart, nrows, threshold, lut, edges, image_stride);
     SM_CUDA(cudaGetLastError());
     return 1;
 }

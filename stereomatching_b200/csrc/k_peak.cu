@@ -9,6 +9,8 @@
 //   mode 2: IADD3 + IMAD     (alu + fma pipes together -- the dual-issue ceiling)
 //   mode 3: LOP3 + IMAD
 // Result: thread-instructions per second (one instruction = one "integer op").
+#include <string.h>
+
 #include "sm_common.cuh"
 
 namespace smb {
@@ -84,6 +86,58 @@ extern "C" int sm_measure_int_peak(int device, int mode, double *gops_per_s)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(out);
+    if (prev >= 0) cudaSetDevice(prev);
+    return SM_OK;
+}
+
+// Host <-> device copy bandwidth of this GPU's link from pinned memory: the ceiling of the
+// end-to-end (host buffers) figure.  mode 0: H2D alone, 1: D2H alone, 2: both directions at
+// once (two streams), reported per direction (H2D in gbs[0], D2H in gbs[1]).
+extern "C" int sm_measure_copy_peak(int device, int mode, double *gbs)
+{
+    SM_REQUIRE(gbs && mode >= 0 && mode <= 2, "sm_measure_copy_peak: bad arguments");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    SM_CUDA(cudaSetDevice(device));
+    const size_t bytes = (size_t)256 << 20;
+    void *h[2] = {nullptr, nullptr}, *d[2] = {nullptr, nullptr};
+    cudaStream_t st[2];
+    cudaEvent_t e0[2], e1[2];
+    for (int k = 0; k < 2; k++) {
+        SM_CUDA(cudaHostAlloc(&h[k], bytes, cudaHostAllocDefault));
+        memset(h[k], k + 1, bytes);
+        SM_CUDA(cudaMalloc(&d[k], bytes));
+        SM_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+        SM_CUDA(cudaEventCreate(&e0[k]));
+        SM_CUDA(cudaEventCreate(&e1[k]));
+    }
+    gbs[0] = gbs[1] = 0.0;
+    for (int rep = 0; rep < 4; rep++) {  // rep 0 is the warm-up
+        for (int k = 0; k < 2; k++) {
+            if (mode != 2 && k != mode) continue;
+            SM_CUDA(cudaEventRecord(e0[k], st[k]));
+            if (k == 0)
+                SM_CUDA(cudaMemcpyAsync(d[0], h[0], bytes, cudaMemcpyHostToDevice, st[0]));
+            else
+                SM_CUDA(cudaMemcpyAsync(h[1], d[1], bytes, cudaMemcpyDeviceToHost, st[1]));
+            SM_CUDA(cudaEventRecord(e1[k], st[k]));
+        }
+        for (int k = 0; k < 2; k++) {
+            if (mode != 2 && k != mode) continue;
+            SM_CUDA(cudaEventSynchronize(e1[k]));
+            float ms = 0;
+            SM_CUDA(cudaEventElapsedTime(&ms, e0[k], e1[k]));
+            const double g = (double)bytes / (ms * 1e-3) / 1e9;
+            if (rep > 0 && g > gbs[k]) gbs[k] = g;
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        cudaEventDestroy(e0[k]);
+        cudaEventDestroy(e1[k]);
+        cudaStreamDestroy(st[k]);
+        cudaFree(d[k]);
+        cudaFreeHost(h[k]);
+    }
     if (prev >= 0) cudaSetDevice(prev);
     return SM_OK;
 }

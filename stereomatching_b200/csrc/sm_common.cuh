@@ -109,7 +109,7 @@ int launch_edges(const T *img, int W, int FH, int ystart, int nrows, int variant
 int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s);
 size_t edge_lut_words();
 int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
-                     const uint32_t *lut, uint8_t *edges, cudaStream_t s);
+                     const uint32_t *lut, uint8_t *edges, cudaStream_t s, int n_images = 1, size_t image_stride = 0);
 
 int launch_fill_web_holes_step(const int32_t *src, int32_t *dst, int W, int H, cudaStream_t s);
 int launch_minmax(const int32_t *a, size_t n, int32_t *d_minmax, cudaStream_t s);

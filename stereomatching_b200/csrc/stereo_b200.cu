@@ -79,7 +79,20 @@ struct sm_ctx {
     uint8_t *scratch_u8 = nullptr;
     int32_t *scratch_i32 = nullptr;
 
-    sm_ctx *shadow = nullptr;  // second pipeline slot of sm_run_batch
+    // sm_run_batch: a three-stage pipeline (H2D | edges + hot path | D2H) over groups of pairs;
+    // NPIPE group buffer sets rotate between the stages
+    static constexpr int NPIPE = 3;
+    struct Pipe {
+        int group = 0;  // pairs per stage
+        cudaStream_t up = nullptr, down = nullptr;
+        uint8_t *img[NPIPE] = {nullptr, nullptr, nullptr};    // [2*group][npix]: first images, then second images
+        uint8_t *edg[NPIPE] = {nullptr, nullptr, nullptr};    // same layout
+        int32_t *web[NPIPE] = {nullptr, nullptr, nullptr};    // [group][npix]
+        int32_t *best[NPIPE] = {nullptr, nullptr, nullptr};   // [group][npix]
+        uint8_t *web8[NPIPE] = {nullptr, nullptr, nullptr};   // [group][npix], only for the u8 result
+        cudaEvent_t ev_up[NPIPE] = {nullptr, nullptr, nullptr}, ev_comp[NPIPE] = {nullptr, nullptr, nullptr},
+                    ev_down[NPIPE] = {nullptr, nullptr, nullptr};
+    } pipe;
 
     size_t npix() const { return (size_t)W * FH; }
 };
@@ -366,8 +379,19 @@ extern "C" int sm_destroy(sm_ctx *c)
 {
     if (!c) return SM_OK;
     DeviceGuard guard(c->device);
-    if (c->shadow) sm_destroy(c->shadow);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (cudaStream_t st : {c->pipe.up, c->pipe.down})
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    for (int k = 0; k < sm_ctx::NPIPE; k++) {
+        void *pp[] = {c->pipe.img[k], c->pipe.edg[k], c->pipe.web[k], c->pipe.best[k], c->pipe.web8[k]};
+        for (void *p : pp)
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : {c->pipe.ev_up[k], c->pipe.ev_comp[k], c->pipe.ev_down[k]})
+            if (e) cudaEventDestroy(e);
+    }
     if (c->edge_lut) cudaFree(c->edge_lut);
     void *ptrs[] = {c->img_u8[0], c->img_u8[1], c->img_f64[0], c->img_f64[1], c->edges[0], c->edges[1],
                     c->best,      c->web,       c->web2,       c->tmp,        c->out,      c->minmax,
@@ -857,29 +881,91 @@ extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const 
     SM_REQUIRE(c->row0 == 0 && c->row1 == c->FH, "sm_run_batch: whole-frame contexts only");
     SM_REQUIRE(!web_u8 || c->D <= 255, "sm_run_batch: u8 web needs num_shifts <= 255");
     SM_REQUIRE(threshold >= 0.0 && threshold <= 1.0, "sm_run_batch: threshold must be between 0 and 1");
-    if (!c->shadow) {
-        int rc = sm_create(&c->shadow, c->device, c->W, c->FH, c->D, c->sw, c->variant);
-        if (rc) return rc;
+    constexpr int NP = sm_ctx::NPIPE;
+    sm_ctx::Pipe &P = c->pipe;
+    const size_t n = c->npix();
+    int rc;
+    if (!P.up) {
+        // pairs per stage: enough for the batched hot path to run in throughput mode, bounded
+        // so that the three buffer sets stay small against HBM (16 B per pixel and pair)
+        P.group = n <= ((size_t)1 << 22) ? 16 : (n <= ((size_t)1 << 24) ? 8 : 2);
+        if (getenv("SMB_PIPE_GROUP")) P.group = atoi(getenv("SMB_PIPE_GROUP"));  // tests: many stages from few pairs
+        if (P.group < 1) P.group = 1;
+        SM_CUDA(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
+        SM_CUDA(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
+        for (int k = 0; k < NP; k++) {
+            if ((rc = dev_alloc(&P.img[k], 2 * P.group * n)) || (rc = dev_alloc(&P.edg[k], 2 * P.group * n)) ||
+                (rc = dev_alloc(&P.web[k], P.group * n)) || (rc = dev_alloc(&P.best[k], P.group * n)))
+                return rc;
+            SM_CUDA(cudaEventCreateWithFlags(&P.ev_up[k], cudaEventDisableTiming));
+            SM_CUDA(cudaEventCreateWithFlags(&P.ev_comp[k], cudaEventDisableTiming));
+            SM_CUDA(cudaEventCreateWithFlags(&P.ev_down[k], cudaEventDisableTiming));
+        }
     }
-    c->shadow->kernel = c->kernel;
-    sm_ctx *slot[2] = {c, c->shadow};
-    size_t n = c->npix();
-    for (int k = 0; k < n_pairs; k++) {
-        sm_ctx *s = slot[k & 1];
-        int rc;
-        // the slot's previous pair (k-2) is complete once its stream has drained up to
-        // here; stream order alone makes reuse of the slot's buffers safe.
-        if ((rc = sm_upload_u8(s, first + (size_t)k * n, second + (size_t)k * n))) return rc;
-        if ((rc = sm_edges(s, threshold))) return rc;
-        if ((rc = sm_match_wta(s))) return rc;
+    if (web_u8)
+        for (int k = 0; k < NP; k++)
+            if ((rc = dev_alloc(&P.web8[k], P.group * n))) return rc;
+    const bool use_lut = !c->edges_fp64_only;
+    if (use_lut && c->lut_threshold != threshold) {
+        if ((rc = dev_alloc(&c->edge_lut, edge_lut_words()))) return rc;
+        if ((rc = launch_edge_lut(threshold, c->edge_lut, c->stream)) < 0) return rc;
+        c->lut_threshold = threshold;
+    }
+    const int G = P.group;
+    int stage = 0, launches = 0;
+    for (int k = 0; k < n_pairs; k += G, stage++) {
+        const int np = n_pairs - k < G ? n_pairs - k : G;
+        const int b = stage % NP;
+        // ---- stage 1, upload stream: the group's images (contiguous in the caller's arrays).
+        // Buffer set b is free once the download of the group that used it last has finished.
+        if (stage >= NP) SM_CUDA(cudaStreamWaitEvent(P.up, P.ev_down[b], 0));
+        SM_CUDA(cudaMemcpyAsync(P.img[b], first + (size_t)k * n, (size_t)np * n, cudaMemcpyHostToDevice, P.up));
+        SM_CUDA(cudaMemcpyAsync(P.img[b] + (size_t)G * n, second + (size_t)k * n, (size_t)np * n,
+                                cudaMemcpyHostToDevice, P.up));
+        SM_CUDA(cudaEventRecord(P.ev_up[b], P.up));
+        // ---- stage 2, the context's stream: edges of all 2*np images, then the batched hot path
+        SM_CUDA(cudaStreamWaitEvent(c->stream, P.ev_up[b], 0));
+        if (use_lut) {
+            // first and second images sit G images apart: one launch each keeps the z-slices dense
+            for (int side = 0; side < 2; side++) {
+                rc = launch_edges_lut(P.img[b] + (size_t)side * G * n, c->W, c->FH, 0, c->FH, c->variant, threshold,
+                                      c->edge_lut, P.edg[b] + (size_t)side * G * n, c->stream, np, n);
+                if (rc < 0) return rc;
+                launches += rc;
+            }
+        } else {
+            for (int j = 0; j < 2 * G; j++) {
+                if (j % G >= np) continue;
+                rc = launch_edges<uint8_t>(P.img[b] + (size_t)j * n, c->W, c->FH, 0, c->FH, c->variant, threshold,
+                                           P.edg[b] + (size_t)j * n, c->stream);
+                if (rc < 0) return rc;
+                launches += rc;
+            }
+        }
+        if ((rc = sm_match_wta_dev_batch(c, np, P.edg[b], P.edg[b] + (size_t)G * n, n, P.best[b], P.web[b], n)))
+            return rc;
+        launches += c->last_launches;
+        if (web_u8) {
+            if ((rc = launch_i32_to_u8(P.web[b], P.web8[b], (size_t)np * n, c->stream)) < 0) return rc;
+            launches += rc;
+        }
+        SM_CUDA(cudaEventRecord(P.ev_comp[b], c->stream));
+        // ---- stage 3, download stream
+        SM_CUDA(cudaStreamWaitEvent(P.down, P.ev_comp[b], 0));
         if (web_u8)
-            rc = queue_web_u8(s, (uint8_t *)web_out + (size_t)k * n);
+            SM_CUDA(cudaMemcpyAsync((uint8_t *)web_out + (size_t)k * n, P.web8[b], (size_t)np * n,
+                                    cudaMemcpyDeviceToHost, P.down));
         else
-            rc = copy_band_d2h(s, (int32_t *)web_out + (size_t)k * n, s->web);
-        if (rc) return rc;
-        if (best_out && (rc = copy_band_d2h(s, best_out + (size_t)k * n, s->best))) return rc;
+            SM_CUDA(cudaMemcpyAsync((int32_t *)web_out + (size_t)k * n, P.web[b], (size_t)np * n * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, P.down));
+        if (best_out)
+            SM_CUDA(cudaMemcpyAsync(best_out + (size_t)k * n, P.best[b], (size_t)np * n * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, P.down));
+        SM_CUDA(cudaEventRecord(P.ev_down[b], P.down));
     }
+    SM_CUDA(cudaStreamSynchronize(P.up));
     SM_CUDA(cudaStreamSynchronize(c->stream));
-    SM_CUDA(cudaStreamSynchronize(c->shadow->stream));
+    SM_CUDA(cudaStreamSynchronize(P.down));
+    c->last_launches = launches;
     return SM_OK;
 }

@@ -271,6 +271,25 @@ def test_run_batch_equals_single_pairs(orc):
             assert np.array_equal(web8[k], wo.astype(np.uint8))
 
 
+def test_run_batch_pipeline_many_stages(orc, monkeypatch):
+    # groups of 2 pairs: 11 pairs = 6 stages over the 3 buffer sets, ragged last stage; two calls on one context
+    monkeypatch.setenv("SMB_PIPE_GROUP", "2")
+    n, w, h, D, sw = 11, 200, 96, 40, 7
+    pairs = [orc.synth_pair(77 + 2 * k, w, h, D) for k in range(n)]
+    first = np.stack([p[0] for p in pairs])
+    second = np.stack([p[1] for p in pairs])
+    for variant in (smb.WRAP, smb.GHOST):
+        with _ctx(w, h, D, sw, variant) as c:
+            web, best = c.run_batch(first, second, THRESHOLD, want_best=True)
+            web8 = c.run_batch(first[::-1].copy(), second[::-1].copy(), THRESHOLD, web_u8=True)
+        for k in range(n):
+            e1 = orc.edges(first[k], THRESHOLD, variant)
+            e2 = orc.edges(second[k], THRESHOLD, variant)
+            bo, wo = orc.match_wta(e1, e2, D, sw, variant)
+            assert np.array_equal(web[k], wo) and np.array_equal(best[k], bo), (variant, k)
+            assert np.array_equal(web8[n - 1 - k], wo.astype(np.uint8)), (variant, k)
+
+
 def test_device_pointer_entry_with_torch(orc):
     torch = pytest.importorskip("torch")
     a, b = load_pair("1-240x135")
