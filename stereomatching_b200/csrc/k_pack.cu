@@ -52,12 +52,21 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
     const uint8_t *p2 = e2 + (size_t)(rowvalid ? y : 0) * g.W;
     const int x0 = wd * 32 - PADL;
     const bool inrow = wd < g.WPR && rowvalid;
-    const bool fast = inrow && x0 >= 0 && x0 + 32 <= g.W && (g.W & 15) == 0 &&
+    // where the word's 32 pixels come from: in WRAP mode a padding word is an image word again
+    // whenever it lands on whole in-row pixels after wrapping (always so when W is a multiple of
+    // 32); in GHOST mode a word wholly outside the image is zero and needs no loads at all
+    int xs = x0;
+    if (VARIANT == SM_WRAP) {
+        xs %= g.W;
+        if (xs < 0) xs += g.W;
+    }
+    const bool outside = VARIANT == SM_GHOST && (x0 + 32 <= 0 || x0 >= g.W);
+    const bool fast = inrow && !outside && xs >= 0 && xs + 32 <= g.W && (g.W & 15) == 0 && (xs & 15) == 0 &&
                       ((reinterpret_cast<uintptr_t>(e1) | reinterpret_cast<uintptr_t>(e2)) & 15) == 0;
     uint32_t l = 0, r = 0, v = 0;
     if (fast) {
-        const uint4 *q1 = reinterpret_cast<const uint4 *>(p1 + x0);
-        const uint4 *q2 = reinterpret_cast<const uint4 *>(p2 + x0);
+        const uint4 *q1 = reinterpret_cast<const uint4 *>(p1 + xs);
+        const uint4 *q2 = reinterpret_cast<const uint4 *>(p2 + xs);
         uint4 a0 = __ldg(q1), a1 = __ldg(q1 + 1), b0 = __ldg(q2), b1 = __ldg(q2 + 1);
         l = gather32(a0, a1);
         r = gather32(b0, b1);
@@ -65,7 +74,7 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
     }
     // padding / ragged / unaligned words: the whole warp builds each one with ballots,
     // lane b supplying pixel b of the word (wrapped or masked per the variant)
-    uint32_t slow = __ballot_sync(0xFFFFFFFFu, inrow && !fast);
+    uint32_t slow = __ballot_sync(0xFFFFFFFFu, inrow && !fast && !outside);
     while (slow) {
         const int k = __ffs(slow) - 1;
         slow &= slow - 1;
