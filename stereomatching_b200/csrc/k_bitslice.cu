@@ -164,8 +164,32 @@ __device__ __forceinline__ uint32_t lop3(uint32_t x, uint32_t y, uint32_t z)
     return r;
 }
 
+// Sum of N one-bit words as bit planes, by carry-save adders: plane K is the parity of the N
+// words of weight 2^K, reduced three at a time (a full adder is two LOP3: sum and majority),
+// and every adder's carry is a word of weight 2^(K+1).  About 2 * (N - planes) LOP3 in all.
+template <int N, int K>
+__device__ __forceinline__ void csa_planes(const uint32_t (&a)[N], uint32_t (&P)[5])
+{
+    constexpr int NC = N / 2;  // carries this level produces
+    uint32_t c[NC > 0 ? NC : 1];
+    uint32_t acc = a[0];
+#pragma unroll
+    for (int i = 1; i + 1 < N; i += 2) {
+        c[(i - 1) / 2] = lop3<0xE8>(acc, a[i], a[i + 1]);  // majority
+        acc = lop3<0x96>(acc, a[i], a[i + 1]);             // parity
+    }
+    if ((N & 1) == 0) {  // one word left over: half adder
+        c[NC - 1] = acc & a[N - 1];
+        acc ^= a[N - 1];
+    }
+    P[K] = acc;
+    if constexpr (NC > 0) csa_planes<NC, K + 1>(c, P);
+}
+
 // One walk of pass A.  VALID_ALL: every pixel of the walk is inside the image (always so in
 // WRAP mode and away from the borders in GHOST mode), so the validity select drops out.
+// The first 2*HALF match words only fill the window: they are summed by a carry-save tree
+// instead of 2*HALF counter steps; from then on one word enters and one leaves per step.
 template <int HALF, int NW, int SEG, bool VALID_ALL>
 __device__ __forceinline__ void walk(const uint32_t (&q)[3], const uint32_t (&lw)[2], const uint32_t (&vw)[2],
                                      uint4 *hq, uint32_t *h5, uint32_t *mq)
@@ -174,13 +198,23 @@ __device__ __forceinline__ void walk(const uint32_t (&q)[3], const uint32_t (&lw
     constexpr int N = C::N, KH = C::KH, STEPS = C::STEPS;
     uint32_t P[5] = {0, 0, 0, 0, 0};
     uint32_t m[STEPS];
-#pragma unroll
-    for (int t = 0; t < STEPS; t++) {
+    auto match_word = [&](int t) {
         const int qi = t >> 5;
         uint32_t mm = __funnelshift_r(q[qi], q[qi + 1 > 2 ? 2 : qi + 1], t & 31);
         if (!(lw[t >> 5] & (1u << (t & 31)))) mm = ~mm;               // L(u) ? R : ~R
         if (!VALID_ALL && !(vw[t >> 5] & (1u << (t & 31)))) mm = 0u;  // taps outside the image count nothing
-        m[t] = mm;
+        if (t >= HALF && t < HALF + SEG) mq[(t - HALF) * NW] = mm;    // centre word of pixel ws*SEG + t - HALF
+        return mm;
+    };
+    if constexpr (HALF > 0) {
+        uint32_t fill[2 * HALF];
+#pragma unroll
+        for (int t = 0; t < 2 * HALF; t++) fill[t] = m[t] = match_word(t);
+        csa_planes<2 * HALF, 0>(fill, P);
+    }
+#pragma unroll
+    for (int t = 2 * HALF; t < STEPS; t++) {
+        const uint32_t mm = m[t] = match_word(t);
         const uint32_t mout = t >= N ? m[t - N] : 0u;
         // up/down counter: +1 where mm & ~mout, -1 where mout & ~mm
         uint32_t c = (mm ^ mout) & (P[0] ^ mout);
@@ -191,11 +225,8 @@ __device__ __forceinline__ void walk(const uint32_t (&q)[3], const uint32_t (&lw
             P[k] ^= c;
             c = cn;
         }
-        if (t >= 2 * HALF) {
-            hq[t - 2 * HALF] = make_uint4(P[0], P[1], P[2], P[3]);
-            if (KH > 4) h5[t - 2 * HALF] = P[4];
-        }
-        if (t >= HALF && t < HALF + SEG) mq[(t - HALF) * NW] = mm;  // centre word of pixel ws*SEG + t - HALF
+        hq[t - 2 * HALF] = make_uint4(P[0], P[1], P[2], P[3]);
+        if (KH > 4) h5[t - 2 * HALF] = P[4];
     }
 }
 

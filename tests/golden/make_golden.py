@@ -8,7 +8,10 @@ src/stereo.c:72,113,184,196 and the stereo-ghost.c twins) through oracle.RefLib 
 records zlib CRC32s of the raw arrays (edges as W*H u8, best/web as little-endian i32),
 the convention of SURVEY.md 8(c).  The committed JSON is what travels to the GPU box.
 
-usage: python tests/golden/make_golden.py [--quick]   (--quick skips 1080p/4K wrap: ~6 min)
+usage: python tests/golden/make_golden.py [--quick] [--fixtures-only NAME]
+       (--quick skips 1080p/4K wrap: ~6 min; --fixtures-only regenerates one fixture's entries)
+
+Fixture 0 is the Tsukuba pair derived from the thesis figure (imgs/0-tsukuba-327x245/PROVENANCE.md).
 """
 import json
 import os
@@ -23,7 +26,7 @@ sys.path.insert(0, ROOT)
 import oracle  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = ["1-240x135", "2-480x270", "3-960x540", "4-1920x1080", "5-3840x2160"]
+FIXTURES = ["0-tsukuba-327x245", "1-240x135", "2-480x270", "3-960x540", "4-1920x1080", "5-3840x2160"]
 THRESHOLD = 0.15
 
 
@@ -57,7 +60,10 @@ def main():
     out = json.load(open(path)) if os.path.exists(path) else {}
     orc = oracle.Oracle()
     # real fixtures, reference defaults (stereo.c:6-10): D=30, sw=21
+    only = sys.argv[sys.argv.index("--fixtures-only") + 1] if "--fixtures-only" in sys.argv else None
     for name in FIXTURES:
+        if only and name != only:
+            continue
         left, right = load(name)
         for variant in (oracle.GHOST, oracle.WRAP):
             big = left.size > 960 * 540
@@ -66,6 +72,8 @@ def main():
             run_case("fixture/%s/%s" % (name, "ghost" if variant else "wrap"), left, right, 30, 21,
                      variant, out)
             json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+    if only:
+        return
     # synthetic config 2: 1920x1080, D=64, sw=9, seed 1234
     left, right, disp = orc.synth_pair(1234, 1920, 1080, 64)
     out["synth/c2/generator"] = {"left": oracle.crc32(left), "right": oracle.crc32(right),

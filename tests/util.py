@@ -6,7 +6,7 @@ from PIL import Image
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 IMGS = os.path.join(ROOT, "tests", "golden", "imgs")
-FIXTURES = ["1-240x135", "2-480x270", "3-960x540", "4-1920x1080", "5-3840x2160"]
+FIXTURES = ["0-tsukuba-327x245", "1-240x135", "2-480x270", "3-960x540", "4-1920x1080", "5-3840x2160"]
 THRESHOLD = 0.15
 
 
