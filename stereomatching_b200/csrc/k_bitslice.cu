@@ -63,6 +63,9 @@ struct WS {
     static constexpr int STEPS = SEG + 2 * HALF;
     static constexpr int H5N = KH > 4 ? ((NR * NW * HROW + 3) & ~3) : 0;  // words, 16-byte multiple
     static constexpr size_t SMEM = (size_t)NR * NW * HROW * 16 + (size_t)H5N * 4 + (size_t)NRM * MROW * 4;
+    // warps (= CTAs) per SM that shared memory allows: ptxas is told, so that it spends the
+    // registers this occupancy leaves free on interleaving independent rows
+    static constexpr int WARPS_PER_SM = (int)((227 * 1024) / (SMEM + 1024)) > 32 ? 32 : (int)((227 * 1024) / (SMEM + 1024));
     static_assert(RB >= 1 && RB * NW * NSEG == 32, "walkers must fill the warp");
     static_assert(STEPS + 32 <= 96 && STEPS < 64, "walker windows: 96 bits of RB, 64 bits of LA/LB");
 };
@@ -284,7 +287,7 @@ __device__ __forceinline__ void store_if(int32_t *p, int v, bool on)
 }
 
 template <int HALF, int NW, int SEG, bool MULTI>
-__global__ void __launch_bounds__(32) k_bitslice(BitsliceArgs a)
+__global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslice(BitsliceArgs a)
 {
     using C = WS<HALF, NW, SEG>;
     constexpr int N = C::N, KH = C::KH, PV = C::PV, TW = C::TW, RB = C::RB, NR = C::NR, NRM = C::NRM;
