@@ -327,6 +327,10 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
         h[4] = KH > 4 ? H5[(slot * NW + w) * HROW + lane] : 0u;
     };
 
+    // launched as the pack kernel's programmatic dependent (HotArgs::after_pack): everything above
+    // overlapped its tail; the packed planes are complete and visible only after this point
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     for (int chunk = 0; chunk < nchunks; chunk++) {
         const int wg0 = chunk * NW;  // first 32-shift word of this chunk
         const int rbit = lbit + 32 * (wg0 + ww);
@@ -523,7 +527,21 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
     a.rows_per_seg = (a.rows_per_seg + C::RB - 1) / C::RB * C::RB;
     segs = (h.g.BH + a.rows_per_seg - 1) / a.rows_per_seg;
     dim3 grid(strips, segs, h.npairs);
-    kern<<<grid, 32, C::SMEM, s>>>(a);
+    if (h.after_pack) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(32);
+        cfg.dynamicSmemBytes = C::SMEM;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SM_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    } else {
+        kern<<<grid, 32, C::SMEM, s>>>(a);
+    }
     SM_CUDA(cudaGetLastError());
     return 1;
 }

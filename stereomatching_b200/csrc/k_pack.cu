@@ -32,6 +32,9 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
        PackedGeom g, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB, uint32_t *__restrict__ RB,
        size_t edge_stride, size_t plane_stride)
 {
+    // let a programmatic dependent (the main kernel, HotArgs::after_pack) be scheduled right away:
+    // it waits (griddepcontrol.wait) for this grid's completion before it reads the planes
+    asm volatile("griddepcontrol.launch_dependents;");
     e1 += blockIdx.z * edge_stride;  // one pair per grid z-slice
     e2 += blockIdx.z * edge_stride;
     LA += blockIdx.z * plane_stride;

@@ -75,6 +75,10 @@ struct HotArgs {
     // words further, its outputs out_stride elements further
     int npairs = 1;
     size_t plane_stride = 0, out_stride = 0;
+    // the pack kernel that produces LA/LB/RB is the launch just before on the same stream: the
+    // main kernel may then start as its programmatic dependent (griddepcontrol), so that its
+    // launch and prologue overlap the pack kernel's tail
+    bool after_pack = false;
 };
 
 // launchers (each returns the number of kernels launched, or a negative sm_status)
