@@ -70,6 +70,8 @@ struct WS {
     static_assert(STEPS + 32 <= 96 && STEPS < 64, "walker windows: 96 bits of RB, 64 bits of LA/LB");
 };
 
+enum { MODE_LAUNCH = 0, MODE_PREPARE = 1, MODE_CANDIDATES = 2 };
+
 struct BitsliceArgs {
     HotArgs h;
     int rows_per_seg;  // output rows per warp
@@ -482,7 +484,7 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
 }
 
 template <int HALF, int NW, int SEG>
-int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
+int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand, int max_cand)
 {
     using C = WS<HALF, NW, SEG>;
     // MULTI: more than one chunk of 32*NW shifts, i.e. (best, web) are merged across passes
@@ -499,7 +501,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
         SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, C::SMEM));
         occ_of_device[dev] = occ > 0 ? occ : 1;
     }
-    if (prepare_only) return 0;  // module loaded, attribute set, occupancy cached
+    if (mode == MODE_PREPARE) return 0;  // module loaded, attribute set, occupancy cached
     const int blocks_per_sm = occ_of_device[dev];
     BitsliceArgs a;
     a.h = h;
@@ -507,10 +509,33 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
     // a run is at least one block of rows.  (Short runs pay 2*half warm-up rows each, but they
     // only happen when the frame is too small to fill the machine, where latency is what counts.)
     const int min_rows = C::RB;
+    const int max_segs = (h.g.BH + min_rows - 1) / min_rows;
+    // a wanted number of runs -> whole blocks of RB rows per run (only the frame's last run has a
+    // ragged, slower block) and the number of runs that results
+    auto shape = [&](int want_segs, int &rows) {
+        int sg = want_segs < 1 ? 1 : (want_segs > max_segs ? max_segs : want_segs);
+        rows = (h.g.BH + sg - 1) / sg;
+        rows = (rows + C::RB - 1) / C::RB * C::RB;
+        return (h.g.BH + rows - 1) / rows;
+    };
+    if (mode == MODE_CANDIDATES) {
+        // launch shapes worth timing for one pair per launch: from half a wave of resident warps
+        // to several waves (short runs pay more window-filling rows, long runs balance worse)
+        const double f[] = {0.5, 0.625, 0.75, 0.875, 1.0, 1.25, 1.5, 2.0, 2.5, 3.0, 4.0};
+        int n = 0;
+        for (double x : f) {
+            int rows, sg = shape((int)(x * num_sms * blocks_per_sm / strips), rows);
+            bool seen = false;
+            for (int k = 0; k < n; k++) seen |= cand[k] == sg;
+            if (!seen && n < max_cand) cand[n++] = sg;
+        }
+        return n;
+    }
     int segs;
     if (h.npairs == 1) {
-        // latency mode (one pair): one full wave of resident warps
-        segs = num_sms * blocks_per_sm / strips;
+        // latency mode (one pair): the shape timed best at sm_create (force_segs), else one full
+        // wave of resident warps
+        segs = h.force_segs > 0 ? h.force_segs : num_sms * blocks_per_sm / strips;
     } else {
         // throughput mode (several pairs per launch): runs of about SMB_TR windows, whatever the
         // number of CTAs -- the launch may be several waves deep, the block scheduler keeps the
@@ -519,13 +544,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
         const int want = tr_env * C::N;
         segs = (h.g.BH + want - 1) / want;
     }
-    if (segs < 1) segs = 1;
-    const int max_segs = (h.g.BH + min_rows - 1) / min_rows;
-    if (segs > max_segs) segs = max_segs;
-    a.rows_per_seg = (h.g.BH + segs - 1) / segs;
-    // whole blocks of RB rows per run: only the frame's last run has a ragged (slower, branchy) block
-    a.rows_per_seg = (a.rows_per_seg + C::RB - 1) / C::RB * C::RB;
-    segs = (h.g.BH + a.rows_per_seg - 1) / a.rows_per_seg;
+    segs = shape(segs, a.rows_per_seg);
     dim3 grid(strips, segs, h.npairs);
     if (h.after_pack) {
         cudaLaunchConfig_t cfg = {};
@@ -552,11 +571,11 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
 constexpr int seg_for(int half, int nw) { return 16; }
 
 template <int NW>
-int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, bool prepare_only)
+int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand = nullptr, int max_cand = 0)
 {
     switch (half) {
 #define SM_CASE(HF) \
-    case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s, prepare_only);
+    case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s, mode, cand, max_cand);
         SM_CASE(0) SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5)
         SM_CASE(6) SM_CASE(7) SM_CASE(8) SM_CASE(9) SM_CASE(10)
 #undef SM_CASE
@@ -575,8 +594,8 @@ static int words_per_pass(const HotArgs &h) { return h.g.D <= 32 ? 1 : 2; }
 
 int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
 {
-    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, s, false);
-    return dispatch_half<2>(h.g.half, h, num_sms, s, false);
+    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, s, MODE_LAUNCH);
+    return dispatch_half<2>(h.g.half, h, num_sms, s, MODE_LAUNCH);
 }
 
 // How many pairs of a batch to put into one launch.  Every warp pays 2*half warm-up rows per
@@ -599,8 +618,16 @@ int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 // occupancy, so that the first sm_match_wta call pays none of that.
 int prepare_bitslice(const HotArgs &h, int num_sms)
 {
-    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, nullptr, true);
-    return dispatch_half<2>(h.g.half, h, num_sms, nullptr, true);
+    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, nullptr, MODE_PREPARE);
+    return dispatch_half<2>(h.g.half, h, num_sms, nullptr, MODE_PREPARE);
+}
+
+// Launch shapes (number of row runs per strip) worth timing for a single-pair launch of this
+// geometry; sm_create times them and keeps the fastest (HotArgs::force_segs).
+int bitslice_seg_candidates(const HotArgs &h, int num_sms, int *cand, int max_cand)
+{
+    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, nullptr, MODE_CANDIDATES, cand, max_cand);
+    return dispatch_half<2>(h.g.half, h, num_sms, nullptr, MODE_CANDIDATES, cand, max_cand);
 }
 
 }  // namespace smb

@@ -79,6 +79,8 @@ struct HotArgs {
     // main kernel may then start as its programmatic dependent (griddepcontrol), so that its
     // launch and prologue overlap the pack kernel's tail
     bool after_pack = false;
+    // one pair per launch: number of row runs per strip (0 = one wave of resident warps)
+    int force_segs = 0;
 };
 
 // launchers (each returns the number of kernels launched, or a negative sm_status)
@@ -89,6 +91,7 @@ int launch_direct(const HotArgs &a, cudaStream_t s);
 int launch_bitslice(const HotArgs &a, int num_sms, cudaStream_t s);
 bool bitslice_supports(int half, int D);
 int prepare_bitslice(const HotArgs &a, int num_sms);
+int bitslice_seg_candidates(const HotArgs &a, int num_sms, int *cand, int max_cand);
 int bitslice_pairs_per_launch(const HotArgs &a, int num_sms, int max_pairs);
 // force the (lazily loaded) kernels of each translation unit into the context
 void warm_edges(int variant);

@@ -44,6 +44,7 @@ struct sm_ctx {
     cudaEvent_t *prof_ev = nullptr;
     int prof_cap = 0, prof_n = 0;
     int last_launches = 0;
+    int tuned_segs = 0;  // single-pair launch shape of the bit-sliced kernel, timed at create (0: default)
 
     // frame-sized device arrays (a band context touches only the rows it needs)
     uint8_t *img_u8[2] = {nullptr, nullptr};
@@ -201,6 +202,7 @@ HotArgs hot_args(sm_ctx *c, int32_t *best, int32_t *web)
     a.best = best;
     a.web = web;
     a.row0 = c->row0;
+    a.force_segs = c->tuned_segs;
     return a;
 }
 
@@ -240,6 +242,45 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
     }
     c->timed = true;
     c->last_launches = launches;
+    return SM_OK;
+}
+
+// Time the single-pair launch shapes the kernel proposes for this geometry (a few launches
+// each, on planes that say "every pixel valid") and keep the fastest: between half a wave and
+// several waves of warps the best run length depends on the frame height, the window and the
+// occupancy in ways a formula misses (measured: 4K / 256 shifts / window 11 is 16 % faster
+// two waves deep, 1080p / window 21 is fastest at exactly one).  Part of the untimed set-up.
+int tune_launch_shape(sm_ctx *c)
+{
+    HotArgs a = hot_args(c, c->best, c->web);
+    int cand[16];
+    const int n = bitslice_seg_candidates(a, c->num_sms, cand, 16);
+    if (n <= 1) return SM_OK;
+    const size_t pw = (size_t)c->g.ER * c->g.WPR;
+    SM_CUDA(cudaMemsetAsync(c->LA, 0xFF, pw * sizeof(uint32_t), c->stream));
+    SM_CUDA(cudaMemsetAsync(c->LB, 0, pw * sizeof(uint32_t), c->stream));
+    SM_CUDA(cudaMemsetAsync(c->RB, 0x5A, pw * sizeof(uint32_t), c->stream));
+    float best_ms = 1e30f;
+    int best_segs = 0;
+    for (int k = 0; k < n; k++) {
+        a.force_segs = cand[k];
+        float tmin = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {  // rep 0 warms up
+            SM_CUDA(cudaEventRecord(c->ev0, c->stream));
+            int rc = launch_bitslice(a, c->num_sms, c->stream);
+            if (rc < 0) return rc;
+            SM_CUDA(cudaEventRecord(c->ev1, c->stream));
+            SM_CUDA(cudaEventSynchronize(c->ev1));
+            float ms = 0;
+            SM_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            if (rep > 0 && ms < tmin) tmin = ms;
+        }
+        if (tmin < best_ms) {
+            best_ms = tmin;
+            best_segs = cand[k];
+        }
+    }
+    c->tuned_segs = best_segs;
     return SM_OK;
 }
 
@@ -365,6 +406,7 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
     if (bitslice_supports(c->half, c->D)) {
         HotArgs a = hot_args(c, c->best, c->web);
         if ((rc = prepare_bitslice(a, c->num_sms)) < 0) return fail(rc);
+        if (!(getenv("SMB_NO_TUNE") && atoi(getenv("SMB_NO_TUNE"))) && (rc = tune_launch_shape(c)) < 0) return fail(rc);
     }
     *out = c;
     return SM_OK;
