@@ -275,10 +275,11 @@ __device__ __forceinline__ void wta(const uint32_t (&V)[NR_][NW][PV], const uint
     }
 #pragma unroll
     for (int k = 0; k < NR_; k++) {
-        idx[k] = 0;
-#pragma unroll
-        for (int w = 0; w < NW; w++)
-            if (cand[k][w]) idx[k] = 32 * w + 31 - __clz(cand[k][w]);  // later words overwrite: highest lane
+        // highest surviving lane; a later word holds higher shifts.  The bit index of an empty
+        // word is -1, and -1 ^ 32 stays negative, so one signed max picks the right word
+        // (word 0 is never empty: it starts as valid[0] != 0 and is only replaced by non-zero t)
+        idx[k] = 31 - __clz(cand[k][0]);
+        if (NW == 2) idx[k] = max(idx[k], (31 - __clz(cand[k][NW - 1])) ^ 32);
     }
 }
 

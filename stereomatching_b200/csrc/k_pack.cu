@@ -32,9 +32,6 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
        PackedGeom g, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB, uint32_t *__restrict__ RB,
        size_t edge_stride, size_t plane_stride)
 {
-    // let a programmatic dependent (the main kernel, HotArgs::after_pack) be scheduled right away:
-    // it waits (griddepcontrol.wait) for this grid's completion before it reads the planes
-    asm volatile("griddepcontrol.launch_dependents;");
     e1 += blockIdx.z * edge_stride;  // one pair per grid z-slice
     e2 += blockIdx.z * edge_stride;
     LA += blockIdx.z * plane_stride;
@@ -104,6 +101,11 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
         LB[o] = ~l & v;
         RB[o] = r & v;
     }
+    // let a programmatic dependent (the main kernel, HotArgs::after_pack) be scheduled while this
+    // grid drains: it waits (griddepcontrol.wait) for this grid's completion before it reads the
+    // planes.  Triggering here rather than at the top keeps the dependent's CTAs from being placed
+    // around this grid's resident CTAs (an uneven placement when the dependent is under one wave)
+    asm volatile("griddepcontrol.launch_dependents;");
 }
 
 int launch_pack(const uint8_t *e1, const uint8_t *e2, int FH, int row0, int variant,

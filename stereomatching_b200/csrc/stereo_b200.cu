@@ -245,43 +245,50 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
     return SM_OK;
 }
 
-// Time the single-pair launch shapes the kernel proposes for this geometry (a few launches
-// each, on planes that say "every pixel valid") and keep the fastest: between half a wave and
-// several waves of warps the best run length depends on the frame height, the window and the
-// occupancy in ways a formula misses (measured: 4K / 256 shifts / window 11 is 16 % faster
-// two waves deep, 1080p / window 21 is fastest at exactly one).  Part of the untimed set-up.
+// Time the single-pair launch shapes the kernel proposes for this geometry and keep the
+// fastest: between half a wave and several waves of warps the best run length depends on the
+// frame height, the window and the occupancy in ways a formula misses (measured: 4K / 256
+// shifts / window 11 is 16 % faster two waves deep, 1080p / window 21 is fastest at exactly
+// one).  What is timed is what callers run: pack + main kernel (programmatic dependent launch)
+// several times back to back, on whatever bytes the edge buffers hold (the kernels are
+// branch-free in the data).  Part of the untimed set-up.
 int tune_launch_shape(sm_ctx *c)
 {
     HotArgs a = hot_args(c, c->best, c->web);
     int cand[16];
     const int n = bitslice_seg_candidates(a, c->num_sms, cand, 16);
     if (n <= 1) return SM_OK;
-    const size_t pw = (size_t)c->g.ER * c->g.WPR;
-    SM_CUDA(cudaMemsetAsync(c->LA, 0xFF, pw * sizeof(uint32_t), c->stream));
-    SM_CUDA(cudaMemsetAsync(c->LB, 0, pw * sizeof(uint32_t), c->stream));
-    SM_CUDA(cudaMemsetAsync(c->RB, 0x5A, pw * sizeof(uint32_t), c->stream));
+    SM_CUDA(cudaMemsetAsync(c->edges[0], 1, c->npix(), c->stream));
+    SM_CUDA(cudaMemsetAsync(c->edges[1], 0, c->npix(), c->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    SM_CUDA(cudaEventCreate(&e0));
+    SM_CUDA(cudaEventCreate(&e1));
     float best_ms = 1e30f;
-    int best_segs = 0;
-    for (int k = 0; k < n; k++) {
-        a.force_segs = cand[k];
+    int best_segs = 0, rc = SM_OK;
+    for (int k = 0; k < n && rc == SM_OK; k++) {
+        c->tuned_segs = cand[k];
         float tmin = 1e30f;
-        for (int rep = 0; rep < 4; rep++) {  // rep 0 warms up
-            SM_CUDA(cudaEventRecord(c->ev0, c->stream));
-            int rc = launch_bitslice(a, c->num_sms, c->stream);
-            if (rc < 0) return rc;
-            SM_CUDA(cudaEventRecord(c->ev1, c->stream));
-            SM_CUDA(cudaEventSynchronize(c->ev1));
+        for (int rep = 0; rep < 3 && rc == SM_OK; rep++) {  // rep 0 warms up
+            const int calls = rep == 0 ? 1 : 4;
+            cudaEventRecord(e0, c->stream);
+            for (int j = 0; j < calls && rc == SM_OK; j++) rc = run_hot(c, c->edges[0], c->edges[1], c->best, c->web);
+            cudaEventRecord(e1, c->stream);
+            if (cudaEventSynchronize(e1) != cudaSuccess) rc = SM_ERR_CUDA;
             float ms = 0;
-            SM_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-            if (rep > 0 && ms < tmin) tmin = ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms / calls < tmin) tmin = ms / calls;
         }
         if (tmin < best_ms) {
             best_ms = tmin;
             best_segs = cand[k];
         }
     }
-    c->tuned_segs = best_segs;
-    return SM_OK;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->tuned_segs = rc == SM_OK ? best_segs : 0;
+    c->timed = false;
+    c->last_launches = 0;
+    return rc;
 }
 
 void profile_free(sm_ctx *c)
