@@ -248,7 +248,8 @@ __device__ __forceinline__ void wta(const uint32_t (&V)[NR_][NW][PV], const uint
     for (int k = 0; k < NR_; k++) {
         best[k] = 0;
 #pragma unroll
-        for (int w = 0; w < NW; w++) cand[k][w] = valid[w];
+        for (int w = 0; w < NW; w++)  // register copy via the FMA pipe: the first plane then is a predicated move like the others
+            asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(cand[k][w]) : "r"(valid[w]), "r"(one));
     }
 #pragma unroll
     for (int p = PV - 1; p >= 0; p--) {
