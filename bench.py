@@ -356,15 +356,28 @@ def run_b200_arm(a, rank, world, local_rank):
         hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md)"
         if os.path.exists(mp_path):
             hbm_peak, hbm_src = float(json.load(open(mp_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
-        traffic = None
+        traffic, prof = None, {}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("main_kernel_dram_bytes_per_launch")
+            prof = json.load(open(tp))
+            traffic = prof.get("main_kernel_dram_bytes_per_launch")
+        # executed (not algorithmic) instruction rate: warp instructions per pair as counted by ncu for the timed
+        # region's launch shape (profiles/) x 32 threads / the per-pair time measured live here
+        issue = None
+        bl = prof.get("batched_launch")
+        if bl and a.kernel in (0, 2):
+            tinstr = bl["warp_instructions"] * 32.0 / bl["pairs"]
+            rate = tinstr / (ms * 1e-3 / a.steps / B) / 1e12
+            issue = {"executed_thread_instr_per_pair": tinstr, "achieved": rate, "peak": peak / 1e3, "unit": "T thread-instr/s",
+                     "frac": rate / (peak / 1e3), "alu_pipe_pct_ncu": bl["alu_pipe_pct_of_peak_active"],
+                     "note": "instruction count and ALU-pipe utilisation from ncu (profiles/r01_final_ncu_full_summary.md), "
+                             "time from this run's timed region; the kernel executes about 2.5 thread instructions per "
+                             "pixel x shift where the algorithmic count assumes 8, hence roofline.frac > 1"}
         achieved = OPS_PER_MDE * W * H * D / main_s / 1e12
         roofline = {
             "bound": "int_alu", "kernel": "bit-sliced match/box/WTA" if ctx.last_launches() else None,
             "achieved": achieved, "peak": peak / 1e3, "unit": "Tiop/s", "frac": achieved / (peak / 1e3),
-            "traffic": traffic,
+            "traffic": traffic, "issue": issue,
             "peak_source": "measured live on this GPU: sm_measure_int_peak, max over instruction mixes %s "
                            "(1e9 thread-instr/s)" % json.dumps({k: round(v) for k, v in peaks.items()}),
             "algorithmic_ops": "%d int ops per pixel x shift (SURVEY 8d) x %d per launch" % (OPS_PER_MDE, W * H * D),
