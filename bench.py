@@ -214,6 +214,18 @@ def run_reference_arm(a, rank):
 # ------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs next to its GPU (NVML's ideal affinity) so that the pinned staging buffers of
+    the end-to-end leg are first-touched on the GPU's own NUMA node.  Best effort; returns what was done."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return "cpus %d-%d (%d)" % (cpus[0], cpus[-1], len(cpus))
+    except Exception as e:  # noqa: BLE001
+        return "not bound: %s" % type(e).__name__
 def run_b200_arm(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -224,6 +236,7 @@ def run_b200_arm(a, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         # control plane only (barrier + max of the per-rank time): the data path has no exchange step,
         # so no NCCL communicator is ever needed; gloo keeps stdout to the one JSON line
@@ -404,7 +417,7 @@ def run_b200_arm(a, rank, world, local_rank):
                        "distinct_pairs": distinct, "frames_per_s": value * 1e6 / (W * H * D),
                        "l2": "every pair has its own input and output buffers: %.1f GB per step, far above the "
                              "126 MB L2" % (B * BYTES_PER_PIXEL * W * H / 1e9),
-                       "parallelism": "whole pairs per GPU, no collective"},
+                       "parallelism": "whole pairs per GPU, no collective", "host_binding_rank0": numa},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "MDE/s", "h2d_bytes_per_step": 2 * Be * W * H,
                     "d2h_bytes_per_step": 4 * Be * W * H, "pairs_per_step": Be, "steps": e2e_steps,
