@@ -215,8 +215,10 @@ int sm_download_web_u8(sm_ctx *ctx, uint8_t *host);
 /* ---- whole pairs, batched (8f n4) ------------------------ */
 
 /* Runs n_pairs independent stereo pairs through upload -> edges -> hot path ->
- * download on ONE context/device with double-buffered streams (upload of pair k+1
- * overlaps compute of pair k).  first/second: n_pairs frames of width*height u8,
+ * download on ONE context/device as a three-stage pipeline over groups of pairs
+ * (H2D of group g+1 | batched edges + hot path of group g | D2H of group g-1, three
+ * streams, three rotating device buffer sets; returns when everything has landed in
+ * web_out).  first/second: n_pairs frames of width*height u8,
  * back to back (pinned memory recommended).  web_out: n_pairs frames of i32 (or u8
  * when web_u8 != 0); best_out may be NULL.  Multi-GPU callers shard pairs over one
  * context per device (pair k -> device k mod n), no cross-device traffic. */
