@@ -580,6 +580,7 @@ int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, int m
     case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s, mode, cand, max_cand);
         SM_CASE(0) SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5)
         SM_CASE(6) SM_CASE(7) SM_CASE(8) SM_CASE(9) SM_CASE(10)
+        SM_CASE(11) SM_CASE(12) SM_CASE(13) SM_CASE(14) SM_CASE(15)
 #undef SM_CASE
     default: set_error("bit-sliced kernel: window half %d not instantiated", half); return SM_ERR_ARG;
     }
@@ -587,8 +588,9 @@ int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, int m
 
 }  // namespace
 
-// square_width up to 21 (the reference default, stereo.c:8); wider windows take the direct kernel.
-bool bitslice_supports(int half, int D) { return half >= 0 && half <= 10 && D >= 1 && D <= 512; }
+// square_width up to 31 (the reference default is 21, stereo.c:8): 5 planes hold a row count of up to 31 and a
+// walk of 16 + 2*15 steps fits the walker's 96-bit window; wider windows take the direct kernel.
+bool bitslice_supports(int half, int D) { return half >= 0 && half <= 15 && D >= 1 && D <= 512; }
 
 // shift words per pass: 2 (64 shifts) unless 32 shifts cover D (one word per pass with more
 // passes was measured slower: 87 vs 60 us on config 4)

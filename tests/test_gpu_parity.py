@@ -128,6 +128,8 @@ GEOMS = [  # (w, h, D, sw): odd widths, W not a multiple of 16/32, sw == min(w,h
     (21, 21, 30, 21), (33, 17, 7, 3), (64, 64, 64, 9), (100, 37, 30, 21), (257, 33, 40, 5),
     (130, 70, 130, 11), (48, 48, 512, 7), (19, 40, 64, 9), (512, 24, 33, 13), (96, 50, 1, 1),
     (200, 45, 96, 15), (77, 31, 31, 17), (640, 40, 256, 11), (35, 35, 65, 2),
+    # windows 23..31: still the bit-sliced kernel (5 row-count planes, 10 box-count planes)
+    (120, 60, 40, 23), (90, 90, 64, 27), (200, 64, 30, 31), (310, 35, 100, 29), (64, 31, 20, 31), (70, 66, 33, 25),
 ]
 
 
@@ -145,6 +147,51 @@ def test_random_edge_maps_odd_geometries(orc, variant, kernel):
             best, web = _run_edges(c, le, re)
         assert np.array_equal(best, bo), (w, h, D, sw)
         assert np.array_equal(web, wo), (w, h, D, sw)
+
+
+def test_windows_beyond_the_bitsliced_kernel(orc):
+    # square_width 33..63: only the direct kernel covers them; AUTO must pick it, forcing the bit-sliced one must fail
+    rng = np.random.default_rng(5)
+    for (w, h, D, sw) in [(96, 70, 30, 33), (80, 64, 17, 63), (150, 45, 64, 45)]:
+        le = (rng.random((h, w)) < 0.4).astype(np.uint8)
+        re = np.roll(le, 5, axis=1) ^ (rng.random((h, w)) < 0.03).astype(np.uint8)
+        for variant in (smb.WRAP, smb.GHOST):
+            bo, wo = orc.match_wta(le, re, D, sw, variant)
+            with _ctx(w, h, D, sw, variant) as c:
+                best, web = _run_edges(c, le, re)
+            assert np.array_equal(best, bo) and np.array_equal(web, wo), (w, h, D, sw, variant)
+    with _ctx(96, 70, 30, 33, smb.WRAP, smb.KERNEL_BITSLICE) as c:
+        with pytest.raises(smb.StereoError):
+            z = np.zeros((70, 96), np.uint8)
+            _run_edges(c, z, z)
+
+
+def test_tuned_and_default_launch_shapes_agree(orc, monkeypatch):
+    # the launch shape timed at sm_create changes how rows are split into runs, never the result
+    w, h, D, sw = 640, 360, 64, 9
+    left, right, _ = orc.synth_pair(4321, w, h, D)
+    for variant in (smb.WRAP, smb.GHOST):
+        e1, e2 = orc.edges(left, THRESHOLD, variant), orc.edges(right, THRESHOLD, variant)
+        res = []
+        for no_tune in ("0", "1"):
+            monkeypatch.setenv("SMB_NO_TUNE", no_tune)
+            with _ctx(w, h, D, sw, variant) as c:
+                res.append(_run_edges(c, e1, e2))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+        bo, wo = orc.match_wta(e1, e2, D, sw, variant)
+        assert np.array_equal(res[0][0], bo) and np.array_equal(res[0][1], wo)
+
+
+def test_run_batch_empty_and_single(orc):
+    w, h, D, sw = 128, 64, 32, 5
+    left, right, _ = orc.synth_pair(9, w, h, D)
+    with _ctx(w, h, D, sw, smb.GHOST) as c:
+        out = c.run_batch(np.zeros((0, h, w), np.uint8), np.zeros((0, h, w), np.uint8), THRESHOLD)
+        assert out.shape == (0, h, w)
+        web8 = c.run_batch(left[None], right[None], THRESHOLD, web_u8=True)
+    e1, e2 = orc.edges(left, THRESHOLD, smb.GHOST), orc.edges(right, THRESHOLD, smb.GHOST)
+    _, wo = orc.match_wta(e1, e2, D, sw, smb.GHOST)
+    assert np.array_equal(web8[0], wo.astype(np.uint8))
 
 
 def test_degenerate_maps(orc):
