@@ -437,3 +437,41 @@ def test_config3_properties(orc):
     bo, wo = orc.match_wta(e1[sl], e2[sl], D, sw, smb.GHOST)
     assert np.array_equal(wo[half:-half], web[y0:y1])
     assert np.array_equal(bo[half:-half], best[y0:y1])
+
+
+def test_config4_properties(orc):
+    """1280x720, D=128, sw=21 (BASELINE config 4, the reference's default window): a batch of whole pairs with
+    seeds 1234 + 2k through sm_run_batch (host buffers, pipelined), u8 and i32 webs, known disparity in tile
+    interiors, the oracle on a horizontal slab of the first and the last pair, batch == one pair at a time."""
+    W, H, D, sw, n = 1280, 720, 128, 21, 19
+    pairs = [orc.synth_pair(1234 + 2 * k, W, H, D) for k in range(n)]
+    first = np.stack([p[0] for p in pairs])
+    second = np.stack([p[1] for p in pairs])
+    half, TW, TH = sw // 2, 4 * D, 120
+    ys, xs = np.mgrid[0:H, 0:W]
+    interior = ((xs % TW >= half) & (xs % TW < TW - D - half) & (ys % TH >= half + 1) &
+                (ys % TH < TH - half - 1) & (xs >= half + 1) & (xs < W - D - half - 1) &
+                (ys >= half + 1) & (ys < H - half - 1))
+    for variant in (smb.WRAP, smb.GHOST):
+        with _ctx(W, H, D, sw, variant) as c:
+            web, best = c.run_batch(first, second, THRESHOLD, want_best=True)
+            web8 = c.run_batch(first, second, THRESHOLD, web_u8=True)
+            c.upload_u8(first[n - 1], second[n - 1])
+            c.edges(THRESHOLD)
+            c.match_wta()
+            assert np.array_equal(c.download(smb.WEB), web[n - 1]) and np.array_equal(c.download(smb.BEST), best[n - 1])
+        assert np.array_equal(web8, web.astype(np.uint8))
+        assert web.min() >= 1 and web.max() <= D and best.min() >= 0 and best.max() <= sw * sw
+        for k in range(n):
+            assert (web[k][interior] == pairs[k][2][interior] + 1).mean() >= 0.999, (variant, k)
+        y0, y1 = 300, 348
+        sl = slice(y0 - half - 1, y1 + half + 1)  # one more row per side for the 3x3 edge stencil
+        for k in (0, n - 1):
+            e1, e2 = orc.edges(first[k][sl], THRESHOLD, smb.GHOST), orc.edges(second[k][sl], THRESHOLD, smb.GHOST)
+            bo, wo = orc.match_wta(e1[1:-1], e2[1:-1], D, sw, variant if variant == smb.GHOST else smb.GHOST)
+            if variant == smb.GHOST:  # a ghost slab is exact vertically in its interior rows and horizontally everywhere
+                assert np.array_equal(wo[half:-half], web[k][y0:y1]), k
+                assert np.array_equal(bo[half:-half], best[k][y0:y1]), k
+            else:                     # wrap differs from ghost only within half + D columns of the left/right border
+                xin = slice(half + 1, W - D - half - 1)  # column 0 and W-1 edges differ between the variants too
+                assert np.array_equal(wo[half:-half, xin], web[k][y0:y1, xin]), k
