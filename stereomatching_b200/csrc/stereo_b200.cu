@@ -397,11 +397,14 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
     }
     c->own_stream = true;
     size_t n = c->npix(), pw = (size_t)c->g.ER * c->g.WPR;
-    if ((rc = dev_alloc(&c->edges[0], n)) || (rc = dev_alloc(&c->edges[1], n)) ||
+    // both edge maps (and, in sm_upload_u8, both images) live in ONE allocation each, second right after first,
+    // so that sm_edges detects the pair in a single launch (grid z = image)
+    if ((rc = dev_alloc(&c->edges[0], 2 * n)) ||
         (rc = dev_alloc(&c->best, n)) || (rc = dev_alloc(&c->web, n)) ||
         (rc = dev_alloc(&c->LA, pw)) || (rc = dev_alloc(&c->LB, pw)) || (rc = dev_alloc(&c->RB, pw)) ||
         (rc = dev_alloc(&c->minmax, 2)))
         return fail(rc);
+    c->edges[1] = c->edges[0] + n;
     // whole-frame contexts run step 3 as well: its buffers belong to the untimed set-up, like
     // the allocations at the top of the reference's algorithm() (stereo.cu:299-306)
     if (row0 == 0 && row1 == frame_height && ((rc = dev_alloc(&c->tmp, n)) || (rc = dev_alloc(&c->out, n))))
@@ -444,7 +447,7 @@ extern "C" int sm_destroy(sm_ctx *c)
             if (e) cudaEventDestroy(e);
     }
     if (c->edge_lut) cudaFree(c->edge_lut);
-    void *ptrs[] = {c->img_u8[0], c->img_u8[1], c->img_f64[0], c->img_f64[1], c->edges[0], c->edges[1],
+    void *ptrs[] = {c->img_u8[0], nullptr,      c->img_f64[0], c->img_f64[1], c->edges[0], nullptr,  // [1] = [0] + npix
                     c->best,      c->web,       c->web2,       c->tmp,        c->out,      c->minmax,
                     c->LA,        c->LB,        c->RB,         c->scratch_u8, c->scratch_i32};
     for (void *p : ptrs)
@@ -517,7 +520,8 @@ extern "C" int sm_upload_u8(sm_ctx *c, const uint8_t *first, const uint8_t *seco
     SM_ENTER(c);
     SM_REQUIRE(first && second, "sm_upload_u8: NULL image");
     int rc, lo, hi;
-    if ((rc = dev_alloc(&c->img_u8[0], c->npix())) || (rc = dev_alloc(&c->img_u8[1], c->npix()))) return rc;
+    if ((rc = dev_alloc(&c->img_u8[0], 2 * c->npix()))) return rc;
+    c->img_u8[1] = c->img_u8[0] + c->npix();
     image_rows(c, &lo, &hi);
     if ((rc = copy_rows_h2d(c, c->img_u8[0], first, lo, hi)) ||
         (rc = copy_rows_h2d(c, c->img_u8[1], second, lo, hi)))
@@ -563,18 +567,21 @@ extern "C" int sm_edges(sm_ctx *c, double threshold)
         if ((rc = launch_edge_lut(threshold, c->edge_lut, c->stream)) < 0) return rc;
         c->lut_threshold = threshold;
     }
-    for (int k = 0; k < 2; k++) {
-        int rc;
-        if (use_lut)
-            rc = launch_edges_lut(c->img_u8[k], c->W, c->FH, ystart, nrows, c->variant, threshold, c->edge_lut,
-                                  c->edges[k], c->stream);
-        else if (c->img_kind == 1)
-            rc = launch_edges<uint8_t>(c->img_u8[k], c->W, c->FH, ystart, nrows, c->variant, threshold,
-                                       c->edges[k], c->stream);
-        else
-            rc = launch_edges<double>(c->img_f64[k], c->W, c->FH, ystart, nrows, c->variant, threshold,
-                                      c->edges[k], c->stream);
+    if (use_lut) {  // both images in one launch: they sit npix apart in one allocation
+        int rc = launch_edges_lut(c->img_u8[0], c->W, c->FH, ystart, nrows, c->variant, threshold, c->edge_lut,
+                                  c->edges[0], c->stream, 2, c->npix());
         if (rc < 0) return rc;
+    } else {
+        for (int k = 0; k < 2; k++) {
+            int rc;
+            if (c->img_kind == 1)
+                rc = launch_edges<uint8_t>(c->img_u8[k], c->W, c->FH, ystart, nrows, c->variant, threshold,
+                                           c->edges[k], c->stream);
+            else
+                rc = launch_edges<double>(c->img_f64[k], c->W, c->FH, ystart, nrows, c->variant, threshold,
+                                          c->edges[k], c->stream);
+            if (rc < 0) return rc;
+        }
     }
     c->have_edges = true;
     return SM_OK;
