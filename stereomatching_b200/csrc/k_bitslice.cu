@@ -35,6 +35,8 @@
 // chunk holds higher shifts, so it wins ties).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "sm_common.cuh"
 
 namespace smb {
@@ -290,7 +292,12 @@ __device__ __forceinline__ void store_if(int32_t *p, int v, bool on)
                  : "memory");
 }
 
-template <int HALF, int NW, int SEG, bool MULTI>
+// C2 ("column pairs", for num_shifts <= 32): the NW = 2 words of a lane are not two shift words of one pixel but
+// the one shift word of TWO pixels, columns x and x + 32 of a 64-column strip.  Rings, walkers and adders are the
+// two-word machinery unchanged; only the column of word w, the shift base and the winner-take-all (one per word)
+// differ.  It runs 32-shift problems at the per-word cost of the two-word kernel (8-row blocks, 17-row rings at
+// window 9) instead of the one-word kernel's 16-row blocks.
+template <int HALF, int NW, int SEG, bool MULTI, bool C2>
 __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslice(BitsliceArgs a)
 {
     using C = WS<HALF, NW, SEG>;
@@ -310,12 +317,14 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
     a.h.web += blockIdx.z * a.h.out_stride;
     const PackedGeom &g = a.h.g;
     const int lane = threadIdx.x;
-    const int x0 = blockIdx.x * TW;
+    static_assert(!C2 || (NW == 2 && !MULTI), "column pairs: two words, one 32-shift chunk");
+    const int x0 = blockIdx.x * (C2 ? TW * NW : TW);
     const int ja = blockIdx.y * a.rows_per_seg;
     const int jb = min(g.BH, ja + a.rows_per_seg);
     if (ja >= jb) return;
     const int ximg = x0 + lane;
     const bool store_ok = ximg < g.W;
+    const bool store_ok2 = ximg + TW < g.W;  // C2: the lane's second pixel
     const int nchunks = MULTI ? (g.D + 32 * NW - 1) / (32 * NW) : 1;
     const int last_pr = jb + 2 * HALF;   // padded rows [ja, last_pr) feed this warp
     const int first_out = ja + 2 * HALF; // the padded row that completes output row ja
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
     // walker role of this lane
     const int ws = lane / (NW * RB), wl = lane - ws * (NW * RB);
     const int wr = wl / NW, ww = wl - wr * NW;
-    const int lbit = PADL + x0 + ws * SEG - HALF;  // first pixel of the walk, as a bit of LA / LB
+    const int lbit = PADL + x0 + ws * SEG - HALF + (C2 ? TW * ww : 0);  // first pixel of the walk, as a bit of LA / LB
 
     auto load_h = [&](int slot, int w, uint32_t (&h)[5]) {
         const uint4 qv = Hq[(slot * NW + w) * HROW + lane];
@@ -337,11 +346,11 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
 
     for (int chunk = 0; chunk < nchunks; chunk++) {
         const int wg0 = chunk * NW;  // first 32-shift word of this chunk
-        const int rbit = lbit + 32 * (wg0 + ww);
+        const int rbit = lbit + 32 * (wg0 + (C2 ? 0 : ww));
         uint32_t valid[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            int lanes = g.D - 32 * (wg0 + w);
+            int lanes = g.D - 32 * (wg0 + (C2 ? 0 : w));
             valid[w] = lanes >= 32 ? 0xFFFFFFFFu : (lanes <= 0 ? 0u : ((1u << lanes) - 1u));
         }
         const int one = valid[0] ? 1 : g.W;  // always 1 (word 0 of a chunk has lanes); opaque to ptxas
@@ -371,6 +380,40 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
             store_if(a.h.best + oidx, best, st);
             store_if(a.h.web + oidx, web, st);
             oidx += g.W;
+        };
+        // C2: the two pixels of a lane (columns ximg and ximg + 32) of one finished row
+        auto put2 = [&](int best0, int idx0, int best1, int idx1) {
+            store_if(a.h.best + oidx, best0, store_ok);
+            store_if(a.h.web + oidx, idx0 + 1, store_ok);
+            store_if(a.h.best + oidx + TW, best1, store_ok2);
+            store_if(a.h.web + oidx + TW, idx1 + 1, store_ok2);
+            oidx += g.W;
+        };
+        // winner-take-all of G rows held as Vs[G][NW][PV] / Ms[G][NW], then the stores: one WTA over both words
+        // of a pixel, or (C2) one per word, the 2*G single-word chains interleaved like rows
+        auto finish_rows = [&](auto gtag, const auto &Vs, const auto &Ms) {
+            constexpr int G_ = decltype(gtag)::value;
+            if constexpr (!C2) {
+                int best[G_], idx[G_];
+                wta<G_, NW, PV>(Vs, Ms, valid, one, best, idx);
+#pragma unroll
+                for (int k = 0; k < G_; k++) put(best[k], idx[k]);
+            } else {
+                uint32_t V1[2 * G_][1][PV], M1[2 * G_][1];
+#pragma unroll
+                for (int k = 0; k < G_; k++)
+#pragma unroll
+                    for (int w = 0; w < 2; w++) {
+                        M1[2 * k + w][0] = Ms[k][w];
+#pragma unroll
+                        for (int p = 0; p < PV; p++) V1[2 * k + w][0][p] = Vs[k][w][p];
+                    }
+                const uint32_t valid1[1] = {valid[0]};
+                int best[2 * G_], idx[2 * G_];
+                wta<2 * G_, 1, PV>(V1, M1, valid1, one, best, idx);
+#pragma unroll
+                for (int k = 0; k < G_; k++) put2(best[2 * k], idx[2 * k], best[2 * k + 1], idx[2 * k + 1]);
+            }
         };
         auto load_m = [&](int mslot_c, uint32_t (&M)[NW]) {
 #pragma unroll
@@ -436,10 +479,7 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
                         }
                         load_m(wrap_m(mslot0 + r + k - HALF), Ms[k]);
                     }
-                    int best[G], idx[G];
-                    wta<G, NW, PV>(Vs, Ms, valid, one, best, idx);
-#pragma unroll
-                    for (int k = 0; k < G; k++) put(best[k], idx[k]);
+                    finish_rows(std::integral_constant<int, G>{}, Vs, Ms);
                 }
             } else {
                 // warm-up rows (window still filling) and the ragged last block
@@ -470,9 +510,7 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
 #pragma unroll
                             for (int p = 0; p < PV; p++) Vs[0][w][p] = V[w][p];
                         load_m(wrap_m(mslot0 + r - HALF), Ms[0]);  // centre row j + HALF
-                        int best[1], idx[1];
-                        wta<1, NW, PV>(Vs, Ms, valid, one, best, idx);
-                        put(best[0], idx[0]);
+                        finish_rows(std::integral_constant<int, 1>{}, Vs, Ms);
                     }
                 }
             }
@@ -485,13 +523,14 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
     }
 }
 
-template <int HALF, int NW, int SEG>
+template <int HALF, int NW, int SEG, bool C2 = false>
 int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand, int max_cand)
 {
     using C = WS<HALF, NW, SEG>;
     // MULTI: more than one chunk of 32*NW shifts, i.e. (best, web) are merged across passes
-    const bool multi = h.g.D > 32 * NW;
-    auto kern = multi ? k_bitslice<HALF, NW, SEG, true> : k_bitslice<HALF, NW, SEG, false>;
+    const bool multi = !C2 && h.g.D > 32 * NW;
+    auto kern = C2 ? k_bitslice<HALF, NW, SEG, false, C2>
+                   : (multi ? k_bitslice<HALF, NW, SEG, true, false> : k_bitslice<HALF, NW, SEG, false, false>);
     static int occ_cache[2][64] = {{0}};  // per instantiation, per MULTI flavour and per device
     int dev = 0;
     SM_CUDA(cudaGetDevice(&dev));
@@ -507,7 +546,8 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *can
     const int blocks_per_sm = occ_of_device[dev];
     BitsliceArgs a;
     a.h = h;
-    const int strips = (h.g.W + C::TW - 1) / C::TW;
+    const int strip_cols = C2 ? C::TW * NW : C::TW;
+    const int strips = (h.g.W + strip_cols - 1) / strip_cols;
     // a run is at least one block of rows.  (Short runs pay 2*half warm-up rows each, but they
     // only happen when the frame is too small to fill the machine, where latency is what counts.)
     const int min_rows = C::RB;
@@ -586,21 +626,48 @@ int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, int m
     }
 }
 
+// column pairs (C2): instantiated for the windows where it was measured faster than one word per lane
+constexpr int C2_MAX_HALF = 6;
+int dispatch_half_c2(int half, const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand, int max_cand)
+{
+    switch (half) {
+#define SM_CASE(HF) \
+    case HF: return launch_one<HF, 2, seg_for(HF, 2), true>(h, num_sms, s, mode, cand, max_cand);
+        SM_CASE(0) SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5) SM_CASE(6)
+#undef SM_CASE
+    default: set_error("bit-sliced kernel: window half %d not instantiated for column pairs", half); return SM_ERR_ARG;
+    }
+}
+
 }  // namespace
 
 // square_width up to 31 (the reference default is 21, stereo.c:8): 5 planes hold a row count of up to 31 and a
 // walk of 16 + 2*15 steps fits the walker's 96-bit window; wider windows take the direct kernel.
 bool bitslice_supports(int half, int D) { return half >= 0 && half <= 15 && D >= 1 && D <= 512; }
 
-// shift words per pass: 2 (64 shifts) unless 32 shifts cover D (one word per pass with more
-// passes was measured slower: 87 vs 60 us on config 4)
-static int words_per_pass(const HotArgs &h) { return h.g.D <= 32 ? 1 : 2; }
-
-int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
+// How a lane's words are used: two shift words of one pixel (64 shifts per pass; one word per pass with more
+// passes was measured slower: 87 vs 60 us on config 4); for num_shifts <= 32 the one shift word of two pixels
+// (column pairs, C2) for windows up to 13 and frames at least one 64-column strip wide, else one word of one
+// pixel.  Measured at 1080p, one pair per launch, 32 shifts: window 9: 19.4 vs 22.9 us, window 13: 22.9 vs 23.7,
+// window 17: 25.8 vs 24.6 (the two-word rings of wide windows leave 5 warps per SM against 8).
+enum { WORDS_ONE = 1, WORDS_TWO_SHIFT = 2, WORDS_TWO_COLUMNS = 3 };
+static int words_mode(const HotArgs &h)
 {
-    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, s, MODE_LAUNCH);
-    return dispatch_half<2>(h.g.half, h, num_sms, s, MODE_LAUNCH);
+    static const int no_c2 = getenv("SMB_NO_C2") ? atoi(getenv("SMB_NO_C2")) : 0;  // experiment hook
+    if (h.g.D > 32) return WORDS_TWO_SHIFT;
+    return (h.g.W >= 64 && h.g.half <= C2_MAX_HALF && !no_c2) ? WORDS_TWO_COLUMNS : WORDS_ONE;
 }
+
+static int dispatch(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand = nullptr, int max_cand = 0)
+{
+    switch (words_mode(h)) {
+    case WORDS_ONE: return dispatch_half<1>(h.g.half, h, num_sms, s, mode, cand, max_cand);
+    case WORDS_TWO_COLUMNS: return dispatch_half_c2(h.g.half, h, num_sms, s, mode, cand, max_cand);
+    default: return dispatch_half<2>(h.g.half, h, num_sms, s, mode, cand, max_cand);
+    }
+}
+
+int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s) { return dispatch(h, num_sms, s, MODE_LAUNCH); }
 
 // How many pairs of a batch to put into one launch.  Every warp pays 2*half warm-up rows per
 // run, so runs should be as long as the frame allows: pairs are added to the launch until one
@@ -609,7 +676,8 @@ int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s)
 int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 {
     // enough pairs that one launch is a few waves of warps (about 8 resident per SM)
-    const int N = 2 * h.g.half + 1, strips = (h.g.W + 31) / 32;
+    const int strip_cols = words_mode(h) == WORDS_TWO_COLUMNS ? 64 : 32;
+    const int N = 2 * h.g.half + 1, strips = (h.g.W + strip_cols - 1) / strip_cols;
     static const int tr_env = getenv("SMB_TR") ? atoi(getenv("SMB_TR")) : 32;
     const int want = tr_env * N;
     const int segs = (h.g.BH + want - 1) / want > 0 ? (h.g.BH + want - 1) / want : 1;
@@ -620,18 +688,13 @@ int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 
 // Loads the kernel this geometry will use, sets its shared-memory attribute and caches its
 // occupancy, so that the first sm_match_wta call pays none of that.
-int prepare_bitslice(const HotArgs &h, int num_sms)
-{
-    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, nullptr, MODE_PREPARE);
-    return dispatch_half<2>(h.g.half, h, num_sms, nullptr, MODE_PREPARE);
-}
+int prepare_bitslice(const HotArgs &h, int num_sms) { return dispatch(h, num_sms, nullptr, MODE_PREPARE); }
 
 // Launch shapes (number of row runs per strip) worth timing for a single-pair launch of this
 // geometry; sm_create times them and keeps the fastest (HotArgs::force_segs).
 int bitslice_seg_candidates(const HotArgs &h, int num_sms, int *cand, int max_cand)
 {
-    if (words_per_pass(h) == 1) return dispatch_half<1>(h.g.half, h, num_sms, nullptr, MODE_CANDIDATES, cand, max_cand);
-    return dispatch_half<2>(h.g.half, h, num_sms, nullptr, MODE_CANDIDATES, cand, max_cand);
+    return dispatch(h, num_sms, nullptr, MODE_CANDIDATES, cand, max_cand);
 }
 
 }  // namespace smb

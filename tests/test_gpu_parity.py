@@ -356,10 +356,11 @@ def test_device_pointer_entry_with_torch(orc):
     assert np.array_equal(best.cpu().numpy(), bo) and np.array_equal(web.cpu().numpy(), wo)
 
 
-def test_device_batch_entry_overlapped_pack(orc):
+@pytest.mark.parametrize("D,sw", [(64, 9), (30, 7)], ids=["two_shift_words", "column_pairs"])
+def test_device_batch_entry_overlapped_pack(orc, D, sw):
     """sm_match_wta_dev_batch: pack of pair k+1 on a second stream; more pairs than plane sets."""
     torch = pytest.importorskip("torch")
-    n, w, h, D, sw = 7, 200, 90, 64, 9
+    n, w, h = 7, 200, 90
     pairs = [orc.synth_pair(500 + k, w, h, D) for k in range(n)]
     for variant in (smb.WRAP, smb.GHOST):
         e1 = np.stack([orc.edges(p[0], THRESHOLD, variant) for p in pairs])
