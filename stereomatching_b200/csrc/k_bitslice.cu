@@ -28,11 +28,18 @@
 // fully autonomous (one warp per CTA, only __syncwarp): it streams down its rows in blocks
 // of RB rows.  Per block: pass A with the 32 lanes as walkers (lane -> segment, row, shift
 // word; every walker reads its own windows of the packed rows straight from global memory,
-// prefetched one block ahead), H rows and centre match words into two small shared-memory
-// rings, then pass B with the 32 lanes as pixel columns.  The H ring keeps RB + 2*half + 1
-// rows so the row leaving the vertical window is still there.  More than 32*NW shifts are
-// processed as successive chunks over the same rows, merging (best, web) in place (a later
-// chunk holds higher shifts, so it wins ties).
+// prefetched one block ahead; the first 2*half words of a walk are summed by a carry-save
+// tree, csa_planes), H rows and centre match words into two small shared-memory rings, then
+// pass B with the 32 lanes as pixel columns.  The H ring keeps RB + 2*half + 1 rows so the row
+// leaving the vertical window is still there.  More than 32*NW shifts are processed as
+// successive chunks over the same rows, merging (best, web) in place (a later chunk holds
+// higher shifts, so it wins ties).  With 32 shifts or fewer the two words of a lane are two
+// pixels instead (C2, 64-column strips).
+//
+// Launching.  Several pairs per launch (grid z) run in the throughput shape: runs of about 32
+// windows, several waves deep.  One pair per launch runs in the shape sm_create timed fastest
+// for the geometry (HotArgs::force_segs, bitslice_seg_candidates), as the programmatic
+// dependent of the pack kernel (griddepcontrol.wait below).  DESIGN.md 4.1 has the numbers.
 #include <stdlib.h>
 
 #include <type_traits>
