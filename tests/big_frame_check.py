@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/big_frame_check.py -- one 7680x4320 pair (the largest frame the reference's survey mentions): the bit-sliced
+"""tests/big_frame_check.py -- one 7680x4320 pair (the largest frame the reference's survey mentions): the bit-sliced
 kernel against the CPU oracle on two horizontal slabs and against a 3-band run; prints timings.  Uses the oracle as
 the checker only."""
 import os, sys, time

@@ -94,7 +94,7 @@ def test_create_validates_arguments_before_touching_the_gpu():
 def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure; the product package and the host drivers must
     not reference it (a product path through the oracle would void every parity claim)."""
-    for base in ("stereomatching_b200", "host", "include"):
+    for base in ("stereomatching_b200", "host", "include", "tools"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
             if "build" in dirpath.split(os.sep):
                 continue

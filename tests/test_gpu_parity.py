@@ -4,6 +4,8 @@ the CPU oracle and the golden CRCs recorded from the unmodified reference.
 Bar: bit-exact (all integer work; the FP64 edge detector must reproduce the reference's
 0/1 decisions exactly, so it is compared array-for-array as well).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -476,3 +478,12 @@ def test_config4_properties(orc):
             else:                     # wrap differs from ghost only within half + D columns of the left/right border
                 xin = slice(half + 1, W - D - half - 1)  # column 0 and W-1 edges differ between the variants too
                 assert np.array_equal(wo[half:-half, xin], web[k][y0:y1, xin]), k
+
+
+def test_fuzz_sample():
+    """A short run of tests/fuzz_gpu.py (random geometries, bands, variants: bit-sliced vs direct kernel vs oracle)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz_gpu.py"), "60", "99"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
