@@ -268,7 +268,7 @@ int tune_launch_shape(sm_ctx *c)
     for (int k = 0; k < n && rc == SM_OK; k++) {
         c->tuned_segs = cand[k];
         float tmin = 1e30f, warm_ms = 0.f;
-        for (int rep = 0; rep < 3 && rc == SM_OK; rep++) {  // rep 0 warms up
+        for (int rep = 0; rep < 4 && rc == SM_OK; rep++) {  // rep 0 warms up
             const int calls = rep == 0 ? 1 : (warm_ms > 0.15f ? 2 : 4);  // long kernels: fewer repeats
             cudaEventRecord(e0, c->stream);
             for (int j = 0; j < calls && rc == SM_OK; j++) rc = run_hot(c, c->edges[0], c->edges[1], c->best, c->web);
