@@ -259,7 +259,7 @@ def run_b200_arm(a, rank, world, local_rank):
         e2[k] = e2[k % distinct]
     best = torch.empty((B, H, W), dtype=torch.int32, device=dev)
     web = torch.empty((B, H, W), dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a created (non-default) stream: the legacy default stream serialises against others
     ctx.set_stream(stream.cuda_stream)
     torch.cuda.synchronize()
     p1, p2, pb, pw = e1.data_ptr(), e2.data_ptr(), best.data_ptr(), web.data_ptr()
@@ -310,6 +310,18 @@ def run_b200_arm(a, rank, world, local_rank):
         ctx.match_wta_dev(p1 + k * n8, p2 + k * n8, pb + k * n32, pw + k * n32)
     n_iso, pack_ms, main_ms = ctx.profile_read()
     ctx.profile_begin(0)
+    # one pair per call as an application with a single stereo pair would run it: pack + dependent main kernel,
+    # calls back to back on one stream (no per-kernel events in between), each pair in its own buffers
+    nsp = min(B, 64)
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in range(4):
+        ctx.match_wta_dev(p1 + k * n8, p2 + k * n8, pb + k * n32, pw + k * n32)
+    es0.record(stream)
+    for k in range(nsp):
+        ctx.match_wta_dev(p1 + k * n8, p2 + k * n8, pb + k * n32, pw + k * n32)
+    es1.record(stream)
+    torch.cuda.synchronize()
+    single_us = es0.elapsed_time(es1) * 1e3 / nsp
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -417,7 +429,11 @@ def run_b200_arm(a, rank, world, local_rank):
                        "distinct_pairs": distinct, "frames_per_s": value * 1e6 / (W * H * D),
                        "l2": "every pair has its own input and output buffers: %.1f GB per step, far above the "
                              "126 MB L2" % (B * BYTES_PER_PIXEL * W * H / 1e9),
-                       "parallelism": "whole pairs per GPU, no collective", "host_binding_rank0": numa},
+                       "parallelism": "whole pairs per GPU, no collective", "host_binding_rank0": numa,
+                       "one_pair_per_call": {"hot_path_us": single_us, "MDE_per_s": W * H * D / single_us,
+                                             "what": "sm_match_wta_dev per pair (pack + dependent main kernel), %d calls "
+                                                     "back to back on one stream, every pair in its own (cache-cold) buffers, rank 0; with one "
+                                                     "pair's buffers reused tools/latency.py measures 29.7 us" % nsp}},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "MDE/s", "h2d_bytes_per_step": 2 * Be * W * H,
                     "d2h_bytes_per_step": 4 * Be * W * H, "pairs_per_step": Be, "steps": e2e_steps,

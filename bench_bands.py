@@ -55,7 +55,7 @@ def main():
     pin_web = smb.PinnedBuffer((H, W), np.int32)
     pin_l.array[:], pin_r.array[:] = left, right
     ctx = smb.StereoContext(W, H, D, SW, variant, device=local_rank, rows=rows)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a created (non-default) stream
     ctx.set_stream(stream.cuda_stream)
 
     def barrier():
