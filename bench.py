@@ -432,8 +432,7 @@ def run_b200_arm(a, rank, world, local_rank):
                        "parallelism": "whole pairs per GPU, no collective", "host_binding_rank0": numa,
                        "one_pair_per_call": {"hot_path_us": single_us, "MDE_per_s": W * H * D / single_us,
                                              "what": "sm_match_wta_dev per pair (pack + dependent main kernel), %d calls "
-                                                     "back to back on one stream, every pair in its own (cache-cold) buffers, rank 0; with one "
-                                                     "pair's buffers reused tools/latency.py measures 29.7 us" % nsp}},
+                                                     "back to back on one stream, every pair in its own (cache-cold) buffers, rank 0" % nsp}},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "MDE/s", "h2d_bytes_per_step": 2 * Be * W * H,
                     "d2h_bytes_per_step": 4 * Be * W * H, "pairs_per_step": Be, "steps": e2e_steps,

@@ -32,6 +32,15 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
        PackedGeom g, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB, uint32_t *__restrict__ RB,
        size_t edge_stride, size_t plane_stride)
 {
+    // Let the programmatic dependent (the main kernel, HotArgs::after_pack) be scheduled right away: it
+    // waits (griddepcontrol.wait) for this grid's completion before it reads the planes, and its launch
+    // latency hides behind this grid's loads.  Measured on config 2, calls back to back: 29.9 us per call
+    // with the edge maps in L2 and 30.4 us with cache-cold edge maps.  Triggering at the END of this
+    // kernel instead gives 29.4 / 38.4 us (and 48 instead of 52 us on config 4 with warm maps): faster
+    // only as long as every call finds its inputs in L2, so the trigger stays here.  sm_create times
+    // the main kernel's launch shapes under this regime (a dependent under one wave of CTAs is placed
+    // around this grid's still-resident CTAs, which some shapes take badly).
+    asm volatile("griddepcontrol.launch_dependents;");
     e1 += blockIdx.z * edge_stride;  // one pair per grid z-slice
     e2 += blockIdx.z * edge_stride;
     LA += blockIdx.z * plane_stride;
@@ -101,18 +110,16 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
         LB[o] = ~l & v;
         RB[o] = r & v;
     }
-    // let a programmatic dependent (the main kernel, HotArgs::after_pack) be scheduled while this
-    // grid drains: it waits (griddepcontrol.wait) for this grid's completion before it reads the
-    // planes.  Triggering here rather than at the top keeps the dependent's CTAs from being placed
-    // around this grid's resident CTAs (an uneven placement when the dependent is under one wave)
-    asm volatile("griddepcontrol.launch_dependents;");
 }
 
 int launch_pack(const uint8_t *e1, const uint8_t *e2, int FH, int row0, int variant,
                 const PackedGeom &g, uint32_t *LA, uint32_t *LB, uint32_t *RB, cudaStream_t s,
                 int npairs, size_t edge_stride, size_t plane_stride)
 {
-    dim3 block(128);
+    // whole warps of words, no idle warps: the main kernel is scheduled as this grid's programmatic dependent
+    // while these CTAs are still resident, and every warp here takes registers its CTAs would otherwise get
+    const int warps = (g.WPR + 31) / 32;
+    dim3 block(32 * (warps < 4 ? warps : 4));
     dim3 grid((g.WPR + block.x - 1) / block.x, g.ER, npairs);
     if (variant == SM_WRAP)
         k_pack<SM_WRAP><<<grid, block, 0, s>>>(e1, e2, FH, row0, g, LA, LB, RB, edge_stride, plane_stride);

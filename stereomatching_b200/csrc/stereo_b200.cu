@@ -231,7 +231,8 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
     launches += rc;
     if (pe) SM_CUDA(cudaEventRecord(pe[1], c->stream));
     HotArgs a = hot_args(c, best, web);
-    a.after_pack = pe == nullptr;  // nothing lies between the two launches unless the per-kernel profile is on
+    static const bool no_pdl = getenv("SMB_NO_PDL") && atoi(getenv("SMB_NO_PDL"));  // experiment hook
+    a.after_pack = pe == nullptr && !no_pdl;  // nothing lies between the two launches unless the per-kernel profile is on
     rc = launch_main(c, a, c->stream);
     if (rc < 0) return rc;
     launches += rc;

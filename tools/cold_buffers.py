@@ -27,3 +27,12 @@ def run(rot_in, rot_out, n=256):
     return ev0.elapsed_time(ev1) * 1e3 / n
 for name, a, b in (("same buffers", 0, 0), ("rotating inputs", 1, 0), ("rotating outputs", 0, 1), ("both rotating", 1, 1)):
     print("%-18s %.2f us per call" % (name, run(a, b)))
+# per-kernel split (events around each kernel: no dependent launch in this mode)
+for name, rot in (("same inputs", 0), ("rotating inputs", 1)):
+    ctx.profile_begin(128)
+    for k in range(128):
+        i = (k % K) if rot else 0
+        ctx.match_wta_dev(e1.data_ptr() + i * n8, e2.data_ptr() + i * n8, best.data_ptr(), web.data_ptr())
+    n, pack_ms, main_ms = ctx.profile_read()
+    ctx.profile_begin(0)
+    print("%-18s pack %.2f us, main %.2f us" % (name, pack_ms * 1e3 / n, main_ms * 1e3 / n))
