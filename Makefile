@@ -34,7 +34,7 @@ CSRC   := stereomatching_b200/csrc
 LIB    := stereomatching_b200/libstereo_b200.so
 KOBJS  := $(patsubst %,$(CSRC)/build/%.o,stereo_b200 k_edges k_pack k_direct k_bitslice k_step3 k_peak)
 
-all: lib $(outdir)/stereopar $(outdir)/stereopar-ghost host/libhostimage.so
+all: lib $(outdir)/stereopar $(outdir)/stereopar-ghost $(outdir)/stereobatch host/libhostimage.so
 
 lib: $(LIB)
 
@@ -56,6 +56,11 @@ $(outdir)/stereopar: host/driver.c host/hostimage.c host/hostimage.h include/ste
 $(outdir)/stereopar-ghost: host/driver.c host/hostimage.c host/hostimage.h include/stereo_b200.h $(LIB) | $(outdir)
 	$(CC) $(CFLAGS) -DSM_VARIANT=1 host/driver.c host/hostimage.c -o $@ \
 	    -Lstereomatching_b200 -lstereo_b200 -Wl,-rpath,'$$ORIGIN/../stereomatching_b200' -lz -lm
+
+# whole pairs over every GPU of the box through the multi-GPU entry of the C ABI (no reference counterpart)
+$(outdir)/stereobatch: host/batch.c include/stereo_b200.h $(LIB) | $(outdir)
+	$(CC) $(CFLAGS) host/batch.c -o $@ \
+	    -Lstereomatching_b200 -lstereo_b200 -Wl,-rpath,'$$ORIGIN/../stereomatching_b200' -lz
 
 # hostimage as a shared object, for the CPU tests of the PNG reader / PPM writer
 host/libhostimage.so: host/hostimage.c host/hostimage.h

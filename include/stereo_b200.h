@@ -225,6 +225,17 @@ int sm_download_web_u8(sm_ctx *ctx, uint8_t *host);
 int sm_run_batch(sm_ctx *ctx, int n_pairs, const uint8_t *first, const uint8_t *second,
                  double threshold, void *web_out, int web_u8, int32_t *best_out);
 
+/* The same over several GPUs of one box (BASELINE config 4: whole pairs sharded across the
+ * GPUs, inputs scattered from the host, no cross-device traffic): one context and one host thread per
+ * entry of devices[] (an id may repeat); slot d runs pairs [n*d/N, n*(d+1)/N) through sm_run_batch. */
+typedef struct sm_multi sm_multi;
+int sm_multi_create(sm_multi **out, const int *devices, int n_devices, int width, int height,
+                    int num_shifts, int square_width, int variant);
+int sm_multi_run_batch(sm_multi *m, int n_pairs, const uint8_t *first, const uint8_t *second,
+                       double threshold, void *web_out, int web_u8, int32_t *best_out);
+int sm_multi_device_count(const sm_multi *m);
+int sm_multi_destroy(sm_multi *m);
+
 /* ---- geometry helpers (host-side, no GPU) --------------------------------------- */
 
 /* Splits frame rows [0,height) into n_bands contiguous bands; band b = [*row0,*row1). */

@@ -31,6 +31,7 @@ SYMBOLS = [
     "sm_profile_begin", "sm_profile_read", "sm_measure_int_peak", "sm_measure_copy_peak",
     "sm_fill_web_holes", "sm_set_web", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
     "sm_run_batch", "sm_band_rows",
+    "sm_multi_create", "sm_multi_run_batch", "sm_multi_device_count", "sm_multi_destroy",
 ]
 
 
@@ -80,6 +81,10 @@ def lib() -> C.CDLL:
         L.sm_download_web_u8.argtypes = [vp, vp]
         L.sm_run_batch.argtypes = [vp, i, vp, vp, d, vp, i, vp]
         L.sm_band_rows.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+        L.sm_multi_create.argtypes = [C.POINTER(vp), C.POINTER(i), i, i, i, i, i, i]
+        L.sm_multi_run_batch.argtypes = [vp, i, vp, vp, d, vp, i, vp]
+        L.sm_multi_device_count.argtypes = [vp]
+        L.sm_multi_destroy.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -282,3 +287,38 @@ class StereoContext:
         self.set_edges(first_edges, second_edges)
         self.match_wta()
         return self.download(BEST), self.download(WEB)
+
+
+class MultiGpuBatch:
+    """sm_multi_*: whole pairs sharded over several GPUs of one box from ONE process (one context and one host
+    thread per entry of `devices`); the C counterpart of launching one rank per GPU."""
+
+    def __init__(self, devices, width, height, num_shifts, square_width, variant=WRAP):
+        self.W, self.H = width, height
+        self._m = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib().sm_multi_create(C.byref(self._m), arr, len(devices), width, height, num_shifts, square_width,
+                                     variant))
+
+    def run_batch(self, first, second, threshold=0.15, web_u8=False, want_best=False, web_out=None):
+        first = np.ascontiguousarray(first, np.uint8)
+        second = np.ascontiguousarray(second, np.uint8)
+        n = first.shape[0]
+        assert first.shape == second.shape == (n, self.H, self.W)
+        if web_out is None:
+            web_out = np.zeros((n, self.H, self.W), np.uint8 if web_u8 else np.int32)
+        best = np.zeros((n, self.H, self.W), np.int32) if want_best else None
+        _check(lib().sm_multi_run_batch(self._m, n, _ptr(first), _ptr(second), threshold, _ptr(web_out), int(web_u8),
+                                        _ptr(best) if want_best else None))
+        return (web_out, best) if want_best else web_out
+
+    def close(self):
+        if self._m:
+            lib().sm_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

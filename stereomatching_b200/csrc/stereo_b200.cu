@@ -8,6 +8,9 @@
 #include <stdlib.h>
 
 #include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "sm_common.cuh"
 
@@ -1026,5 +1029,86 @@ extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const 
     SM_CUDA(cudaStreamSynchronize(c->stream));
     SM_CUDA(cudaStreamSynchronize(P.down));
     c->last_launches = launches;
+    return SM_OK;
+}
+
+// ---- whole pairs over several GPUs of one box ------------------------------------------------
+//
+// pairs shard with no exchange step.  One context and one host thread per device; device d
+// takes a contiguous range of the batch (the caller's arrays are contiguous, so every stage of its
+// sm_run_batch pipeline stays a single copy).  No cross-device traffic, no collective.
+
+struct sm_multi {
+    int n = 0;
+    sm_ctx **ctx = nullptr;
+};
+
+extern "C" int sm_multi_create(sm_multi **out, const int *devices, int n_devices, int width, int height,
+                               int num_shifts, int square_width, int variant)
+{
+    SM_REQUIRE(out && devices && n_devices >= 1 && n_devices <= 64, "sm_multi_create: bad arguments");
+    *out = nullptr;
+    sm_multi *m = new (std::nothrow) sm_multi;
+    if (!m) {
+        set_error("sm_multi_create: out of memory");
+        return SM_ERR_NOMEM;
+    }
+    m->ctx = (sm_ctx **)calloc((size_t)n_devices, sizeof(sm_ctx *));
+    if (!m->ctx) {
+        delete m;
+        set_error("sm_multi_create: out of memory");
+        return SM_ERR_NOMEM;
+    }
+    m->n = n_devices;
+    for (int d = 0; d < n_devices; d++) {
+        int rc = sm_create(&m->ctx[d], devices[d], width, height, num_shifts, square_width, variant);
+        if (rc) {
+            for (int k = 0; k < d; k++) sm_destroy(m->ctx[k]);
+            free(m->ctx);
+            delete m;
+            return rc;
+        }
+    }
+    *out = m;
+    return SM_OK;
+}
+
+extern "C" int sm_multi_destroy(sm_multi *m)
+{
+    if (!m) return SM_OK;
+    for (int d = 0; d < m->n; d++) sm_destroy(m->ctx[d]);
+    free(m->ctx);
+    delete m;
+    return SM_OK;
+}
+
+extern "C" int sm_multi_device_count(const sm_multi *m) { return m ? m->n : SM_ERR_ARG; }
+
+extern "C" int sm_multi_run_batch(sm_multi *m, int n_pairs, const uint8_t *first, const uint8_t *second,
+                                  double threshold, void *web_out, int web_u8, int32_t *best_out)
+{
+    SM_REQUIRE(m && n_pairs >= 0 && first && second && web_out, "sm_multi_run_batch: bad arguments");
+    const int N = m->n;
+    std::vector<int> rcs((size_t)N, SM_OK);
+    std::vector<std::string> errs((size_t)N);
+    std::vector<std::thread> threads;
+    const size_t n = m->ctx[0]->npix();
+    for (int d = 0; d < N; d++) {
+        const int k0 = (int)((long long)n_pairs * d / N), k1 = (int)((long long)n_pairs * (d + 1) / N);
+        threads.emplace_back([=, &rcs, &errs]() {
+            if (k1 <= k0) return;
+            uint8_t *w8 = (uint8_t *)web_out;
+            void *wout = web_u8 ? (void *)(w8 + (size_t)k0 * n) : (void *)((int32_t *)web_out + (size_t)k0 * n);
+            rcs[d] = sm_run_batch(m->ctx[d], k1 - k0, first + (size_t)k0 * n, second + (size_t)k0 * n, threshold, wout,
+                                  web_u8, best_out ? best_out + (size_t)k0 * n : nullptr);
+            if (rcs[d]) errs[d] = sm_last_error();  // the message is per thread: carry it to the caller's
+        });
+    }
+    for (auto &t : threads) t.join();
+    for (int d = 0; d < N; d++)
+        if (rcs[d]) {
+            set_error("sm_multi_run_batch: device slot %d: %s", d, errs[d].c_str());
+            return rcs[d];
+        }
     return SM_OK;
 }

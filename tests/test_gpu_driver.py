@@ -105,3 +105,26 @@ def test_degenerate_contour_is_reported(tmp_path):
                        capture_output=True, text=True)
     # flat images: web is 30 everywhere, (max-min)/lines == 0; the reference divides by zero
     assert r.returncode != 0 and "divides by zero" in r.stderr
+
+
+def test_stereobatch_c_program_over_all_gpus():
+    """timing/stereobatch (host/batch.c): whole pairs sharded over every visible GPU from C through sm_multi_*;
+    its CRC of the returned webs must equal the oracle's webs of the same synthetic pairs."""
+    import zlib
+    exe = os.path.join(ROOT, "timing", "stereobatch")
+    assert os.path.exists(exe), "run `make build=timing` (or __graft_entry__.build())"
+    orc = oracle.Oracle()
+    w, h, D, sw, n = 320, 180, 64, 9, 7
+    for vname_, variant in (("wrap", 0), ("ghost", 1)):
+        for kind, dt in (("i32", np.int32), ("u8", np.uint8)):
+            r = subprocess.run([exe, str(w), str(h), str(D), str(sw), str(n), vname_, kind], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            fields = dict(kv.split(" = ") for kv in r.stdout.strip().split(", "))
+            assert int(fields["pairs"]) == n and float(fields["elapsed"]) > 0 and int(fields["gpus"]) >= 1
+            webs = []
+            for k in range(n):
+                left, right, _ = orc.synth_pair(1234 + 2 * k, w, h, D)
+                e1, e2 = orc.edges(left, THRESHOLD, variant), orc.edges(right, THRESHOLD, variant)
+                webs.append(orc.match_wta(e1, e2, D, sw, variant)[1].astype(dt))
+            crc = "%08x" % (zlib.crc32(np.stack(webs).tobytes()) & 0xFFFFFFFF)
+            assert fields["web_crc32"] == crc, (vname_, kind, r.stdout)

@@ -487,3 +487,28 @@ def test_fuzz_sample():
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz_gpu.py"), "60", "99"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_multi_gpu_batch_entry(orc):
+    """sm_multi_run_batch: the batch sharded over device slots from one process (one host thread per slot).  With one
+    GPU visible the two slots are two contexts on device 0; with more, one slot per GPU.  Ragged shards, u8 and i32."""
+    ndev = smb.device_count()
+    devices = list(range(ndev)) if ndev >= 2 else [0, 0]
+    if len(devices) == 2:
+        devices = devices + [devices[0]]  # three slots: 11 pairs -> shards of 3, 4, 4
+    n, w, h, D, sw = 11, 320, 180, 64, 9
+    pairs = [orc.synth_pair(300 + 2 * k, w, h, D) for k in range(n)]
+    first = np.stack([p[0] for p in pairs])
+    second = np.stack([p[1] for p in pairs])
+    for variant in (smb.WRAP, smb.GHOST):
+        with smb.MultiGpuBatch(devices, w, h, D, sw, variant) as m:
+            web, best = m.run_batch(first, second, THRESHOLD, want_best=True)
+            web8 = m.run_batch(first, second, THRESHOLD, web_u8=True)
+            one = m.run_batch(first[:1], second[:1], THRESHOLD)  # fewer pairs than slots
+        with _ctx(w, h, D, sw, variant) as c:
+            web_1, best_1 = c.run_batch(first, second, THRESHOLD, want_best=True)
+        assert np.array_equal(web, web_1) and np.array_equal(best, best_1)
+        assert np.array_equal(web8, web_1.astype(np.uint8)) and np.array_equal(one[0], web_1[0])
+        e1, e2 = orc.edges(first[n - 1], THRESHOLD, variant), orc.edges(second[n - 1], THRESHOLD, variant)
+        bo, wo = orc.match_wta(e1, e2, D, sw, variant)
+        assert np.array_equal(web[n - 1], wo) and np.array_equal(best[n - 1], bo)
