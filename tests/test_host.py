@@ -151,3 +151,14 @@ def test_driver_argument_handling(drivers, tmp_path):
         assert run(a, b, "0.15", "136") == (1, "error: square width must not be higher than image width/height\n")
         rc, err = run(a, "nope.png")
         assert rc == 1 and err.startswith("error reading image nope.png:")
+
+
+def test_stereobatch_argument_handling():
+    """host/batch.c: usage and argument errors come before any GPU work (exit 1, message on stderr)."""
+    exe = os.path.join(ROOT, "timing", "stereobatch")
+    if not os.path.exists(exe):
+        pytest.skip("timing/stereobatch not built (make build=timing)")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("usage: ")
+    r = subprocess.run([exe, "64", "64", "16"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("usage: ")
