@@ -177,3 +177,19 @@ def test_step3(orc):
     holes[10:12, 10:12] = 0
     f2 = orc.fill_web_holes(holes, 3)
     assert f2.shape == web.shape
+
+
+@pytest.mark.parametrize("variant", [oracle.WRAP, oracle.GHOST])
+def test_oracle_equals_reference_wide_windows(orc, variant):
+    """Windows beyond the reference default (23..63): the GPU tests use the oracle as checker there too, so the
+    oracle is pinned to the reference's own functions for them (small frames: the reference does sw*sw taps)."""
+    for (w, h, D, sw) in [(120, 60, 30, 23), (90, 90, 64, 27), (200, 64, 30, 31), (96, 70, 30, 33), (80, 64, 16, 63),
+                          (150, 45, 64, 45)]:
+        if not oracle.ref_available(variant, D):
+            pytest.skip("oracle/_ref not built")
+        rng = np.random.default_rng(w + sw)
+        le = (rng.random((h, w)) < 0.4).astype(np.uint8)
+        re = np.roll(le, 5, axis=1) ^ (rng.random((h, w)) < 0.03).astype(np.uint8)
+        br, wr = oracle.RefLib(variant, D).match_wta(le, re, sw)
+        bo, wo = orc.match_wta(le, re, D, sw, variant)
+        assert np.array_equal(bo, br) and np.array_equal(wo, wr), (w, h, D, sw)
