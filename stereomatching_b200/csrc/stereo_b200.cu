@@ -1095,14 +1095,19 @@ extern "C" int sm_multi_run_batch(sm_multi *m, int n_pairs, const uint8_t *first
     const size_t n = m->ctx[0]->npix();
     for (int d = 0; d < N; d++) {
         const int k0 = (int)((long long)n_pairs * d / N), k1 = (int)((long long)n_pairs * (d + 1) / N);
-        threads.emplace_back([=, &rcs, &errs]() {
+        auto work = [=, &rcs, &errs]() {
             if (k1 <= k0) return;
             uint8_t *w8 = (uint8_t *)web_out;
             void *wout = web_u8 ? (void *)(w8 + (size_t)k0 * n) : (void *)((int32_t *)web_out + (size_t)k0 * n);
             rcs[d] = sm_run_batch(m->ctx[d], k1 - k0, first + (size_t)k0 * n, second + (size_t)k0 * n, threshold, wout,
                                   web_u8, best_out ? best_out + (size_t)k0 * n : nullptr);
             if (rcs[d]) errs[d] = sm_last_error();  // the message is per thread: carry it to the caller's
-        });
+        };
+        try {
+            threads.emplace_back(work);
+        } catch (...) {  // no thread to be had: this slot's shard runs on the calling thread
+            work();
+        }
     }
     for (auto &t : threads) t.join();
     for (int d = 0; d < N; d++)
