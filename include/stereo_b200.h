@@ -236,6 +236,17 @@ int sm_multi_run_batch(sm_multi *m, int n_pairs, const uint8_t *first, const uin
 int sm_multi_device_count(const sm_multi *m);
 int sm_multi_destroy(sm_multi *m);
 
+/* ONE pair as row bands over several GPUs of one box (BASELINE config 3): slot g owns output rows
+ * sm_band_rows(height, N, g), uploads them plus half + 1 halo rows per side, and writes only its own rows of the
+ * caller's frame-sized web_out / best_out (best_out may be NULL).  One band context (sm_create_band) and one host
+ * thread per entry of devices[]; no exchange between GPUs. */
+typedef struct sm_bands sm_bands;
+int sm_bands_create(sm_bands **out, const int *devices, int n_devices, int width, int height,
+                    int num_shifts, int square_width, int variant);
+int sm_bands_run(sm_bands *b, const uint8_t *first, const uint8_t *second, double threshold,
+                 int32_t *web_out, int32_t *best_out);
+int sm_bands_destroy(sm_bands *b);
+
 /* ---- geometry helpers (host-side, no GPU) --------------------------------------- */
 
 /* Splits frame rows [0,height) into n_bands contiguous bands; band b = [*row0,*row1). */

@@ -32,6 +32,7 @@ SYMBOLS = [
     "sm_fill_web_holes", "sm_set_web", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
     "sm_run_batch", "sm_band_rows",
     "sm_multi_create", "sm_multi_run_batch", "sm_multi_device_count", "sm_multi_destroy",
+    "sm_bands_create", "sm_bands_run", "sm_bands_destroy",
 ]
 
 
@@ -85,6 +86,9 @@ def lib() -> C.CDLL:
         L.sm_multi_run_batch.argtypes = [vp, i, vp, vp, d, vp, i, vp]
         L.sm_multi_device_count.argtypes = [vp]
         L.sm_multi_destroy.argtypes = [vp]
+        L.sm_bands_create.argtypes = [C.POINTER(vp), C.POINTER(i), i, i, i, i, i, i]
+        L.sm_bands_run.argtypes = [vp, vp, vp, d, vp, vp]
+        L.sm_bands_destroy.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -316,6 +320,38 @@ class MultiGpuBatch:
         if self._m:
             lib().sm_multi_destroy(self._m)
             self._m = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+class MultiGpuBands:
+    """sm_bands_*: ONE pair split into row bands (with replicated halo rows) over several GPUs from one process."""
+
+    def __init__(self, devices, width, height, num_shifts, square_width, variant=WRAP):
+        self.W, self.H = width, height
+        self._b = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib().sm_bands_create(C.byref(self._b), arr, len(devices), width, height, num_shifts, square_width,
+                                     variant))
+
+    def run(self, first, second, threshold=0.15, want_best=False):
+        first = np.ascontiguousarray(first, np.uint8)
+        second = np.ascontiguousarray(second, np.uint8)
+        assert first.shape == second.shape == (self.H, self.W)
+        web = np.zeros((self.H, self.W), np.int32)
+        best = np.zeros((self.H, self.W), np.int32) if want_best else None
+        _check(lib().sm_bands_run(self._b, _ptr(first), _ptr(second), threshold, _ptr(web),
+                                  _ptr(best) if want_best else None))
+        return (web, best) if want_best else web
+
+    def close(self):
+        if self._b:
+            lib().sm_bands_destroy(self._b)
+            self._b = C.c_void_p()
 
     def __enter__(self):
         return self

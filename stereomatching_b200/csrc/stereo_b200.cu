@@ -1117,3 +1117,89 @@ extern "C" int sm_multi_run_batch(sm_multi *m, int n_pairs, const uint8_t *first
         }
     return SM_OK;
 }
+
+// ---- one pair, row bands over several GPUs of one box ----------------------------------------------
+//
+// SURVEY 8e, BASELINE config 3: GPU g owns output rows sm_band_rows(height, N, g); it uploads those rows of
+// both images plus half + 1 halo rows per side (wrapped for WRAP, clipped for GHOST), detects the edges of its
+// rows plus half, runs the hot path on its band and writes only its own rows of web / best into the caller's
+// frame-sized host arrays.  One band context and one host thread per device slot; no exchange step.
+
+struct sm_bands {
+    int n = 0;
+    sm_ctx **ctx = nullptr;
+};
+
+extern "C" int sm_bands_destroy(sm_bands *b)
+{
+    if (!b) return SM_OK;
+    for (int d = 0; d < b->n; d++) sm_destroy(b->ctx[d]);
+    free(b->ctx);
+    delete b;
+    return SM_OK;
+}
+
+extern "C" int sm_bands_create(sm_bands **out, const int *devices, int n_devices, int width, int height,
+                               int num_shifts, int square_width, int variant)
+{
+    SM_REQUIRE(out && devices && n_devices >= 1 && n_devices <= 64, "sm_bands_create: bad arguments");
+    SM_REQUIRE(height >= n_devices, "sm_bands_create: fewer rows than bands");
+    *out = nullptr;
+    sm_bands *b = new (std::nothrow) sm_bands;
+    if (!b) {
+        set_error("sm_bands_create: out of memory");
+        return SM_ERR_NOMEM;
+    }
+    b->ctx = (sm_ctx **)calloc((size_t)n_devices, sizeof(sm_ctx *));
+    if (!b->ctx) {
+        delete b;
+        set_error("sm_bands_create: out of memory");
+        return SM_ERR_NOMEM;
+    }
+    b->n = n_devices;
+    for (int d = 0; d < n_devices; d++) {
+        int r0 = 0, r1 = 0;
+        int rc = sm_band_rows(height, n_devices, d, &r0, &r1);
+        if (!rc) rc = sm_create_band(&b->ctx[d], devices[d], width, height, r0, r1, num_shifts, square_width, variant);
+        if (rc) {
+            sm_bands_destroy(b);  // sm_destroy(NULL) is a no-op for the slots not created yet
+            return rc;
+        }
+    }
+    *out = b;
+    return SM_OK;
+}
+
+extern "C" int sm_bands_run(sm_bands *b, const uint8_t *first, const uint8_t *second, double threshold,
+                            int32_t *web_out, int32_t *best_out)
+{
+    SM_REQUIRE(b && first && second && web_out, "sm_bands_run: bad arguments");
+    const int N = b->n;
+    std::vector<int> rcs((size_t)N, SM_OK);
+    std::vector<std::string> errs((size_t)N);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < N; d++) {
+        auto work = [=, &rcs, &errs]() {
+            sm_ctx *c = b->ctx[d];
+            int rc = sm_upload_u8(c, first, second);  // a band context copies only the rows it needs
+            if (!rc) rc = sm_edges(c, threshold);
+            if (!rc) rc = sm_match_wta(c);
+            if (!rc) rc = sm_download(c, SM_WEB, 0, web_out);  // ... and writes only its own rows
+            if (!rc && best_out) rc = sm_download(c, SM_BEST, 0, best_out);
+            rcs[d] = rc;
+            if (rc) errs[d] = sm_last_error();
+        };
+        try {
+            threads.emplace_back(work);
+        } catch (...) {
+            work();
+        }
+    }
+    for (auto &t : threads) t.join();
+    for (int d = 0; d < N; d++)
+        if (rcs[d]) {
+            set_error("sm_bands_run: band %d: %s", d, errs[d].c_str());
+            return rcs[d];
+        }
+    return SM_OK;
+}

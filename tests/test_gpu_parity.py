@@ -512,3 +512,21 @@ def test_multi_gpu_batch_entry(orc):
         e1, e2 = orc.edges(first[n - 1], THRESHOLD, variant), orc.edges(second[n - 1], THRESHOLD, variant)
         bo, wo = orc.match_wta(e1, e2, D, sw, variant)
         assert np.array_equal(web[n - 1], wo) and np.array_equal(best[n - 1], bo)
+
+
+def test_multi_gpu_bands_entry(orc):
+    """sm_bands_run: one pair as row bands over device slots from one process; equals the whole-frame context and
+    the oracle (3 and 5 bands, both variants; with one GPU visible the slots are band contexts on device 0)."""
+    ndev = smb.device_count()
+    w, h, D, sw = 320, 190, 64, 9
+    left, right, _ = orc.synth_pair(4242, w, h, D)
+    for variant in (smb.WRAP, smb.GHOST):
+        e1, e2 = orc.edges(left, THRESHOLD, variant), orc.edges(right, THRESHOLD, variant)
+        bo, wo = orc.match_wta(e1, e2, D, sw, variant)
+        for nb in (3, 5):
+            devices = [k % ndev for k in range(nb)]
+            with smb.MultiGpuBands(devices, w, h, D, sw, variant) as b:
+                web, best = b.run(left, right, THRESHOLD, want_best=True)
+                web2 = b.run(left, right, THRESHOLD)  # a second frame through the same band contexts
+            assert np.array_equal(web, wo) and np.array_equal(best, bo), (variant, nb)
+            assert np.array_equal(web2, wo)
