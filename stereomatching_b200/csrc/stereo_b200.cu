@@ -311,7 +311,7 @@ void profile_free(sm_ctx *c)
 
 extern "C" const char *sm_last_error(void) { return g_err; }
 
-extern "C" int sm_version(void) { return (1 << 16) | 0; }
+extern "C" int sm_version(void) { return (1 << 16) | 1; }  // 1.1: sm_measure_copy_peak, sm_multi_*, sm_bands_*
 
 extern "C" int sm_device_count(void)
 {
