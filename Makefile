@@ -15,6 +15,11 @@ CC      := gcc
 NVCC    := nvcc
 SM_ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(SM_ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall
+# make DEV=1 lib: development build with the experiment hooks (SMB_* environment variables) and extra
+# kernel instantiations compiled in; the shipped library has none of them
+ifeq ($(DEV),1)
+    NVFLAGS += -DSMB_DEV
+endif
 CFLAGS  := -Wall -Wextra -std=gnu11 -Wno-unused-parameter -Iinclude
 
 ifeq ($(build),debug)

@@ -57,7 +57,21 @@ __host__ __device__ constexpr int bits_for(int v)
     return b;
 }
 
-template <int HALF, int NW, int SEG>
+__host__ __device__ constexpr int pow2_at_least(int v)
+{
+    int p = 32;
+    while (p < v) p *= 2;
+    return p;
+}
+
+// TM: the rows of the vertical window live in TENSOR MEMORY (the 256 KB per SM that tcgen05 normally uses for MMA
+// accumulators), not in shared memory.  A lane of pass B only ever re-reads what IT stored 2*half+1 rows earlier,
+// which is exactly the access pattern of tcgen05.ld/st.32x32b (thread i <-> TMEM lane i): the leaving row's
+// H planes are read back from the lane's own TMEM columns and the entering row's are written over them.  Shared memory
+// then holds only the RB rows of a block (the walker -> column transposition) and the centre-match ring, which
+// is what lifts the 5-plane windows (17..21) from 5 to 8 warps per SM.  A warp reaches only TMEM lanes
+// 32*(warp%4)..+31, hence four warps (four strips) per CTA, one allocation per CTA.
+template <int HALF, int NW, int SEG, bool TM = false>
 struct WS {
     static constexpr int N = 2 * HALF + 1;       // window side
     static constexpr int KH = bits_for(N);       // planes of a horizontal count (<= N)
@@ -65,26 +79,126 @@ struct WS {
     static constexpr int TW = 32;                // pixel columns per warp
     static constexpr int NSEG = TW / SEG;        // walkers per (row, word)
     static constexpr int RB = 32 / (NW * NSEG);  // rows per block: 32 walkers
-    static constexpr int NR = RB + N;            // H ring rows
+    static constexpr int NR = TM ? RB : RB + N;  // H rows in shared memory: the block (TM) or the ring
     static constexpr int NRM = RB + HALF + 1;    // centre-match ring rows
     static constexpr int HROW = TW + 1;          // uint4 per (ring row, word); +1 staggers banks
-    static constexpr int MROW = TW * NW + 2;     // words per M ring row (even: LDS.64 stays aligned)
+    // words per M ring row, +stagger; two words per lane: even, so that the LDS.64 stays aligned
+    static constexpr int MROW = NW == 1 ? TW + 1 : TW * NW + 2;
     static constexpr int STEPS = SEG + 2 * HALF;
     static constexpr int H5N = KH > 4 ? ((NR * NW * HROW + 3) & ~3) : 0;  // words, 16-byte multiple
-    static constexpr size_t SMEM = (size_t)NR * NW * HROW * 16 + (size_t)H5N * 4 + (size_t)NRM * MROW * 4;
-    // warps (= CTAs) per SM that shared memory allows: ptxas is told, so that it spends the
+    static constexpr int MQN = (NRM * MROW + 3) & ~3;                     // words, 16-byte multiple
+    static constexpr size_t SMEM = (size_t)NR * NW * HROW * 16 + (size_t)H5N * 4 + (size_t)MQN * 4;  // per warp
+    static constexpr int WPC = TM ? 4 : 1;                                // warps per CTA
+    static constexpr size_t SMEM_CTA = WPC * SMEM + (TM ? 16 : 0);        // + the TMEM base address slot
+    static constexpr int EC = NW * KH;                                    // TMEM columns per ring row
+    static constexpr int TCOLS = pow2_at_least(N * EC);                   // allocation: a power of two >= 32
+    static constexpr int CTAS_SMEM = (int)((227 * 1024) / (SMEM_CTA + 1024));
+    static constexpr int CTAS_TMEM = TM ? 512 / TCOLS : 64;
+    static constexpr int CTAS_PER_SM_ = CTAS_SMEM < CTAS_TMEM ? CTAS_SMEM : CTAS_TMEM;
+    static constexpr int CTAS_PER_SM = CTAS_PER_SM_ * WPC > 32 ? 32 / WPC : (CTAS_PER_SM_ < 1 ? 1 : CTAS_PER_SM_);
+    // warps per SM that shared memory (and TMEM) allow: ptxas is told, so that it spends the
     // registers this occupancy leaves free on interleaving independent rows
-    static constexpr int WARPS_PER_SM = (int)((227 * 1024) / (SMEM + 1024)) > 32 ? 32 : (int)((227 * 1024) / (SMEM + 1024));
+    static constexpr int WARPS_PER_SM = CTAS_PER_SM * WPC;
+    // dynamic shared memory to ask for: never more co-resident CTAs than TMEM allocations fit (a CTA that cannot
+    // allocate would sit on its shared memory and registers, spinning in tcgen05.alloc)
+    static constexpr size_t SMEM_REQ = !TM ? SMEM_CTA
+        : (SMEM_CTA > (size_t)(227 * 1024) / (CTAS_PER_SM + 1) ? SMEM_CTA : (size_t)(227 * 1024) / (CTAS_PER_SM + 1) + 16);
     static_assert(RB >= 1 && RB * NW * NSEG == 32, "walkers must fill the warp");
     static_assert(STEPS + 32 <= 96 && STEPS < 64, "walker windows: 96 bits of RB, 64 bits of LA/LB");
+    static_assert(!TM || N * EC <= 512, "the vertical window must fit one TMEM allocation");
 };
 
 enum { MODE_LAUNCH = 0, MODE_PREPARE = 1, MODE_CANDIDATES = 2 };
+
+// throughput mode (several pairs per launch): a warp's run of rows, in windows
+inline int throughput_run_windows()
+{
+#ifdef SMB_DEV
+    if (getenv("SMB_TR")) return atoi(getenv("SMB_TR"));
+#endif
+    return 32;
+}
 
 struct BitsliceArgs {
     HotArgs h;
     int rows_per_seg;  // output rows per warp
 };
+
+
+// ---- tensor memory as a lane-private ring (tcgen05.ld/st.32x32b: thread i <-> TMEM lane i) ---------------------
+__device__ __forceinline__ void tm_ld(uint32_t a, uint32_t &r0)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r0) : "r"(a));
+}
+__device__ __forceinline__ void tm_ld(uint32_t a, uint32_t &r0, uint32_t &r1)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+__device__ __forceinline__ void tm_ld(uint32_t a, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void tm_ld(uint32_t a, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t &r4,
+                                      uint32_t &r5, uint32_t &r6, uint32_t &r7)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7) : "r"(a));
+}
+__device__ __forceinline__ void tm_st(uint32_t a, uint32_t r0)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(a), "r"(r0) : "memory");
+}
+__device__ __forceinline__ void tm_st(uint32_t a, uint32_t r0, uint32_t r1)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(a), "r"(r0), "r"(r1) : "memory");
+}
+__device__ __forceinline__ void tm_st(uint32_t a, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st(uint32_t a, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
+                                      uint32_t r5, uint32_t r6, uint32_t r7)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(a), "r"(r0),
+                 "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7)
+                 : "memory");
+}
+
+// EC consecutive columns of the lane, as the power-of-two pieces the instruction offers (10 = 8 + 2, 5 = 4 + 1, ...)
+template <int EC>
+__device__ __forceinline__ void tm_load(uint32_t a, uint32_t (&v)[EC])
+{
+    static_assert(EC >= 1 && EC <= 15, "ring row of at most 15 columns");
+    constexpr int o4 = EC & 8, o2 = o4 + (EC & 4), o1 = o2 + (EC & 2);
+    if constexpr ((EC & 8) != 0) tm_ld(a, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    if constexpr ((EC & 4) != 0) tm_ld(a + o4, v[o4], v[o4 + 1], v[o4 + 2], v[o4 + 3]);
+    if constexpr ((EC & 2) != 0) tm_ld(a + o2, v[o2], v[o2 + 1]);
+    if constexpr ((EC & 1) != 0) tm_ld(a + o1, v[o1]);
+}
+
+template <int EC>
+__device__ __forceinline__ void tm_store(uint32_t a, const uint32_t (&v)[EC])
+{
+    constexpr int o4 = EC & 8, o2 = o4 + (EC & 4), o1 = o2 + (EC & 2);
+    if constexpr ((EC & 8) != 0) tm_st(a, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    if constexpr ((EC & 4) != 0) tm_st(a + o4, v[o4], v[o4 + 1], v[o4 + 2], v[o4 + 3]);
+    if constexpr ((EC & 2) != 0) tm_st(a + o2, v[o2], v[o2 + 1]);
+    if constexpr ((EC & 1) != 0) tm_st(a + o1, v[o1]);
+}
+
+// the loads are asynchronous: the registers may be used only after the wait.  The empty asm statements tie
+// every loaded register to a point after the wait (volatile asm statements keep their order), so that the
+// compiler cannot schedule a use above it.
+template <int EC>
+__device__ __forceinline__ void tm_pin(uint32_t (&v)[EC])
+{
+#pragma unroll
+    for (int k = 0; k < EC; k++) asm volatile("" : "+r"(v[k]));
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // V (PV planes) += H (KH planes), ripple carry; the sum always fits PV planes.
 template <int PV, int KH>
@@ -204,11 +318,11 @@ __device__ __forceinline__ void csa_planes(const uint32_t (&a)[N], uint32_t (&P)
 // WRAP mode and away from the borders in GHOST mode), so the validity select drops out.
 // The first 2*HALF match words only fill the window: they are summed by a carry-save tree
 // instead of 2*HALF counter steps; from then on one word enters and one leaves per step.
-template <int HALF, int NW, int SEG, bool VALID_ALL>
+template <int HALF, int NW, int SEG, bool VALID_ALL, bool TM>
 __device__ __forceinline__ void walk(const uint32_t (&q)[3], const uint32_t (&lw)[2], const uint32_t (&vw)[2],
                                      uint4 *hq, uint32_t *h5, uint32_t *mq)
 {
-    using C = WS<HALF, NW, SEG>;
+    using C = WS<HALF, NW, SEG, TM>;
     constexpr int N = C::N, KH = C::KH, STEPS = C::STEPS;
     uint32_t P[5] = {0, 0, 0, 0, 0};
     uint32_t m[STEPS];
@@ -304,17 +418,39 @@ __device__ __forceinline__ void store_if(int32_t *p, int v, bool on)
 // two-word machinery unchanged; only the column of word w, the shift base and the winner-take-all (one per word)
 // differ.  It runs 32-shift problems at the per-word cost of the two-word kernel (8-row blocks, 17-row rings at
 // window 9) instead of the one-word kernel's 16-row blocks.
-template <int HALF, int NW, int SEG, bool MULTI, bool C2>
-__global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslice(BitsliceArgs a)
+template <int HALF, int NW, int SEG, bool MULTI, bool C2, bool TM>
+__global__ void __launch_bounds__(32 * WS<HALF, NW, SEG, TM>::WPC, WS<HALF, NW, SEG, TM>::CTAS_PER_SM)
+k_bitslice(BitsliceArgs a)
 {
-    using C = WS<HALF, NW, SEG>;
+    using C = WS<HALF, NW, SEG, TM>;
     constexpr int N = C::N, KH = C::KH, PV = C::PV, TW = C::TW, RB = C::RB, NR = C::NR, NRM = C::NRM;
-    constexpr int HROW = C::HROW, MROW = C::MROW, STEPS = C::STEPS;
+    constexpr int HROW = C::HROW, MROW = C::MROW, STEPS = C::STEPS, EC = C::EC, WPC = C::WPC;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4 *Hq = reinterpret_cast<uint4 *>(smem_raw);                   // [NR][NW][HROW]
+    const int warp = TM ? (int)(threadIdx.x >> 5) : 0;  // one strip per warp; the warps of a CTA share nothing but
+    const int lane = threadIdx.x & 31;                  // the TMEM allocation
+    unsigned char *smem_w = smem_raw + (TM ? 16 : 0) + (size_t)warp * C::SMEM;
+    uint4 *Hq = reinterpret_cast<uint4 *>(smem_w);                     // [NR][NW][HROW]
     uint32_t *H5 = reinterpret_cast<uint32_t *>(Hq + NR * NW * HROW);  // [NR][NW][HROW] (KH == 5)
     uint32_t *Mq = H5 + C::H5N;                                        // [NRM][MROW], word (x, w) at x*NW + w
+
+    // TM: one TMEM allocation per CTA (warp 0 allocates, everybody reads the address after a barrier);
+    // this warp's ring row s is columns [s*EC, (s+1)*EC) of its own 32 lanes
+    uint32_t tring = 0;
+    if constexpr (TM) {
+        uint32_t *slot = reinterpret_cast<uint32_t *>(smem_raw);
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(slot)),
+                         "r"((uint32_t)C::TCOLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tring = *slot + ((uint32_t)(warp * 32) << 16);
+    }
 
     // one pair per grid z-slice
     a.h.LA += blockIdx.z * a.h.plane_stride;
@@ -323,12 +459,10 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
     a.h.best += blockIdx.z * a.h.out_stride;
     a.h.web += blockIdx.z * a.h.out_stride;
     const PackedGeom &g = a.h.g;
-    const int lane = threadIdx.x;
     static_assert(!C2 || (NW == 2 && !MULTI), "column pairs: two words, one 32-shift chunk");
-    const int x0 = blockIdx.x * (C2 ? TW * NW : TW);
+    const int x0 = (blockIdx.x * WPC + warp) * (C2 ? TW * NW : TW);
     const int ja = blockIdx.y * a.rows_per_seg;
     const int jb = min(g.BH, ja + a.rows_per_seg);
-    if (ja >= jb) return;
     const int ximg = x0 + lane;
     const bool store_ok = ximg < g.W;
     const bool store_ok2 = ximg + TW < g.W;  // C2: the lane's second pixel
@@ -346,12 +480,28 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
         h[0] = qv.x, h[1] = qv.y, h[2] = qv.z, h[3] = qv.w;
         h[4] = KH > 4 ? H5[(slot * NW + w) * HROW + lane] : 0u;
     };
+    // TM: the KH planes of both words of a ring row <-> EC consecutive TMEM columns
+    auto to_cols = [&](const uint32_t (&h)[NW][5], uint32_t (&e)[EC]) {
+#pragma unroll
+        for (int w = 0; w < NW; w++)
+#pragma unroll
+            for (int k = 0; k < KH; k++) e[w * KH + k] = h[w][k];
+    };
+    auto from_cols = [&](const uint32_t (&e)[EC], uint32_t (&h)[NW][5]) {
+#pragma unroll
+        for (int w = 0; w < NW; w++)
+#pragma unroll
+            for (int k = 0; k < 5; k++) h[w][k] = k < KH ? e[w * KH + k] : 0u;
+    };
 
     // launched as the pack kernel's programmatic dependent (HotArgs::after_pack): everything above
     // overlapped its tail; the packed planes are complete and visible only after this point
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    for (int chunk = 0; chunk < nchunks; chunk++) {
+    // a warp whose strip lies beyond the frame (the last CTA of a row of strips) or whose run is empty has
+    // nothing to do but to take part in the barriers of the TMEM allocation
+    const bool has_work = ja < jb && x0 < g.W;
+    for (int chunk = 0; has_work && chunk < nchunks; chunk++) {
         const int wg0 = chunk * NW;  // first 32-shift word of this chunk
         const int rbit = lbit + 32 * (wg0 + (C2 ? 0 : ww));
         uint32_t valid[NW];
@@ -366,11 +516,21 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
         for (int w = 0; w < NW; w++) {
 #pragma unroll
             for (int p = 0; p < PV; p++) V[w][p] = 0;
-            // ring slot NR-1 stands for padded row ja-1: all zero, so that the first output row
+            // ring slot NR-1 (TM: N-1) stands for padded row ja-1: all zero, so that the first output row
             // may subtract it like any other
-            Hq[((NR - 1) * NW + w) * HROW + lane] = make_uint4(0, 0, 0, 0);
-            if (KH > 4) H5[((NR - 1) * NW + w) * HROW + lane] = 0u;
+            if constexpr (!TM) {
+                Hq[((NR - 1) * NW + w) * HROW + lane] = make_uint4(0, 0, 0, 0);
+                if (KH > 4) H5[((NR - 1) * NW + w) * HROW + lane] = 0u;
+            }
         }
+        if constexpr (TM) {
+            uint32_t z[EC];
+#pragma unroll
+            for (int k = 0; k < EC; k++) z[k] = 0u;
+            tm_wait_st();  // (the previous chunk's last rows)
+            tm_store<EC>(tring + (N - 1) * EC, z);
+        }
+        int tslot = 0;  // TM: ring row of padded row p0 (= (p0 - ja) mod N)
 
         WalkRaw in = {};
         if (ja + wr < last_pr) load_walk_raw(in, a.h, ja + wr, rbit, lbit);
@@ -379,14 +539,21 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
         // arithmetic then is one multiply-add per store (FMA pipe) instead of 64-bit pointer adds
         int oidx = (a.h.row0 + ja) * g.W + ximg;
 
-        // store NR_ finished rows (best, idx) and advance the output pointers
-        auto put = [&](int best, int idx) {
+        // store a finished row (best, idx) and advance the output pointers.  MULTI: a later chunk holds higher
+        // shifts, so it wins ties against what the earlier chunks left in `best` (prev)
+        auto put = [&](int best, int idx, int prev) {
             const int web = 32 * wg0 + idx + 1;
             bool st = store_ok;
-            if (MULTI && chunk != 0 && st) st = best >= a.h.best[oidx];  // a later chunk wins ties (higher shifts)
+            if (MULTI && chunk != 0) st = st && best >= prev;
             store_if(a.h.best + oidx, best, st);
             store_if(a.h.web + oidx, web, st);
             oidx += g.W;
+        };
+        // what the earlier chunks left in `best` for the next output row + k (only read where it is stored)
+        auto load_prev = [&](int k) {
+            int v = 0;
+            if (MULTI && chunk != 0 && store_ok) v = a.h.best[oidx + k * g.W];
+            return v;
         };
         // C2: the two pixels of a lane (columns ximg and ximg + 32) of one finished row
         auto put2 = [&](int best0, int idx0, int best1, int idx1) {
@@ -398,13 +565,13 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
         };
         // winner-take-all of G rows held as Vs[G][NW][PV] / Ms[G][NW], then the stores: one WTA over both words
         // of a pixel, or (C2) one per word, the 2*G single-word chains interleaved like rows
-        auto finish_rows = [&](auto gtag, const auto &Vs, const auto &Ms) {
+        auto finish_rows = [&](auto gtag, const auto &Vs, const auto &Ms, const int *prev) {
             constexpr int G_ = decltype(gtag)::value;
             if constexpr (!C2) {
                 int best[G_], idx[G_];
                 wta<G_, NW, PV>(Vs, Ms, valid, one, best, idx);
 #pragma unroll
-                for (int k = 0; k < G_; k++) put(best[k], idx[k]);
+                for (int k = 0; k < G_; k++) put(best[k], idx[k], prev[k]);
             } else {
                 uint32_t V1[2 * G_][1][PV], M1[2 * G_][1];
 #pragma unroll
@@ -430,14 +597,23 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
         auto wrap_hi = [](int x, int n) { return (int)min((unsigned)x, (unsigned)(x - n)); };
         auto wrap_lo = [](int x, int n) { return (int)min((unsigned)x, (unsigned)(x + n)); };
         auto wrap_m = [&](int ms) { return ms < 0 ? ms + NRM : (ms >= NRM ? ms - NRM : ms); };
+        // TM ring row of x = tslot + r, tslot < N, r < RB
+        auto wrap_t = [&](int x) { return N >= RB ? wrap_hi(x, N) : x % N; };
 
         for (int p0 = ja; p0 < last_pr; p0 += RB) {
             const int nrows = min(RB, last_pr - p0);
+            const bool steady = p0 >= first_out && nrows == RB;
+
+            // MULTI: the earlier chunks' `best` of the rows this block finishes, asked for now so that the loads
+            // are back long before the stores that depend on them (they used to be one exposed L2 round trip per row)
+            int prev[RB];
+#pragma unroll
+            for (int r = 0; r < RB; r++) prev[r] = steady ? load_prev(r) : 0;
 
             // ---------------- pass A: 32 walkers ----------------
             {
                 const bool active = wr < nrows;
-                int slot = slot0 + wr;
+                int slot = TM ? wr : slot0 + wr;
                 slot = slot >= NR ? slot - NR : slot;
                 int mslot = mslot0 + wr;
                 mslot = mslot >= NRM ? mslot - NRM : mslot;
@@ -453,9 +629,9 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
                 const unsigned long long vl = (((unsigned long long)vw[1]) << 32) | vw[0];
                 const bool all_valid = (~vl & ((1ull << STEPS) - 1ull)) == 0ull;
                 if (__all_sync(0xFFFFFFFFu, all_valid || !active)) {
-                    if (active) walk<HALF, NW, SEG, true>(q, lw, vw, hq, h5, mq);
+                    if (active) walk<HALF, NW, SEG, true, TM>(q, lw, vw, hq, h5, mq);
                 } else {
-                    if (active) walk<HALF, NW, SEG, false>(q, lw, vw, hq, h5, mq);
+                    if (active) walk<HALF, NW, SEG, false, TM>(q, lw, vw, hq, h5, mq);
                 }
             }
             __syncwarp();
@@ -464,60 +640,105 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
             if (p0 + RB + wr < last_pr) load_walk_raw(in, a.h, p0 + RB + wr, rbit, lbit);
 
             // ---------------- pass B: 32 pixel columns ----------------
-            if (p0 >= first_out && nrows == RB) {
+            if (steady) {
                 // steady state, branch-free: every row enters, one leaves, one output row.
                 // Rows go in groups of G so that their winner-take-all chains interleave.
                 constexpr int G = (RB % 4 == 0) ? 4 : ((RB % 2 == 0) ? 2 : 1);
+                constexpr int GT = TM && N < G ? 1 : G;  // TM: a group's rows must be distinct ring rows
 #pragma unroll
                 for (int r = 0; r < RB; r += G) {
                     uint32_t Vs[G][NW][PV], Ms[G][NW];
+                    uint32_t eo[G][EC];  // TM: the leaving rows, as read back from tensor memory
+                    int ts[G];
+                    if constexpr (TM) {
+#pragma unroll
+                        for (int k = 0; k < G; k++) ts[k] = wrap_t(tslot + r + k);
+                        if (GT == G) {
+                            tm_wait_st();  // a ring row written by an earlier group is complete before it is re-read
+#pragma unroll
+                            for (int k = 0; k < G; k++) tm_load<EC>(tring + ts[k] * EC, eo[k]);
+                            tm_wait_ld();
+#pragma unroll
+                            for (int k = 0; k < G; k++) tm_pin<EC>(eo[k]);
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < G; k++) {
-                        const int slot_n = wrap_hi(slot0 + r + k, NR);
-                        const int slot_o = wrap_lo(slot_n - N, NR);
+                        uint32_t hn[NW][5], ho[NW][5];
+                        if constexpr (TM) {
+                            if (GT != G) {
+                                tm_wait_st();
+                                tm_load<EC>(tring + ts[k] * EC, eo[k]);
+                                tm_wait_ld();
+                                tm_pin<EC>(eo[k]);
+                            }
+                            from_cols(eo[k], ho);
+#pragma unroll
+                            for (int w = 0; w < NW; w++) load_h(r + k, w, hn[w]);
+                            uint32_t en[EC];
+                            to_cols(hn, en);
+                            tm_store<EC>(tring + ts[k] * EC, en);  // the entering row takes the leaving row's place
+                        } else {
+                            const int slot_n = wrap_hi(slot0 + r + k, NR);
+                            const int slot_o = wrap_lo(slot_n - N, NR);
+#pragma unroll
+                            for (int w = 0; w < NW; w++) {
+                                load_h(slot_n, w, hn[w]);
+                                load_h(slot_o, w, ho[w]);
+                            }
+                        }
 #pragma unroll
                         for (int w = 0; w < NW; w++) {
-                            uint32_t hn[5], ho[5];
-                            load_h(slot_n, w, hn);
-                            load_h(slot_o, w, ho);
-                            planes_addsub<PV, KH>(V[w], hn, ho);
+                            planes_addsub<PV, KH>(V[w], hn[w], ho[w]);
 #pragma unroll
                             for (int p = 0; p < PV; p++) Vs[k][w][p] = V[w][p];
                         }
                         load_m(wrap_m(mslot0 + r + k - HALF), Ms[k]);
                     }
-                    finish_rows(std::integral_constant<int, G>{}, Vs, Ms);
+                    finish_rows(std::integral_constant<int, G>{}, Vs, Ms, prev + r);
                 }
             } else {
                 // warm-up rows (window still filling) and the ragged last block
                 for (int r = 0; r < nrows; r++) {
-                    int slot_n = slot0 + r;
+                    int slot_n = TM ? r : slot0 + r;
                     slot_n = slot_n >= NR ? slot_n - NR : slot_n;
+                    const int pr = p0 + r;
+                    uint32_t hn[NW][5], ho[NW][5];
+#pragma unroll
+                    for (int w = 0; w < NW; w++) load_h(slot_n, w, hn[w]);
+                    if constexpr (TM) {
+                        const int t = wrap_t(tslot + r);
+                        if (pr > first_out) {  // padded row pr - N left the window: it is what ring row t holds
+                            uint32_t eo[EC];
+                            tm_wait_st();
+                            tm_load<EC>(tring + t * EC, eo);
+                            tm_wait_ld();
+                            tm_pin<EC>(eo);
+                            from_cols(eo, ho);
+                        }
+                        uint32_t en[EC];
+                        to_cols(hn, en);
+                        tm_store<EC>(tring + t * EC, en);
+                    } else if (pr > first_out) {
+                        int slot_o = slot_n - N;
+                        slot_o = slot_o < 0 ? slot_o + NR : slot_o;
+#pragma unroll
+                        for (int w = 0; w < NW; w++) load_h(slot_o, w, ho[w]);
+                    }
 #pragma unroll
                     for (int w = 0; w < NW; w++) {
-                        uint32_t hn[5];
-                        load_h(slot_n, w, hn);
-                        planes_add<PV, KH>(V[w], hn);
+                        planes_add<PV, KH>(V[w], hn[w]);
+                        if (pr > first_out) planes_sub<PV, KH>(V[w], ho[w]);
                     }
-                    const int pr = p0 + r;
                     if (pr >= first_out) {
-                        if (pr > first_out) {
-                            int slot_o = slot_n - N;  // padded row j-1 left the window
-                            slot_o = slot_o < 0 ? slot_o + NR : slot_o;
-#pragma unroll
-                            for (int w = 0; w < NW; w++) {
-                                uint32_t ho[5];
-                                load_h(slot_o, w, ho);
-                                planes_sub<PV, KH>(V[w], ho);
-                            }
-                        }
                         uint32_t Vs[1][NW][PV], Ms[1][NW];
 #pragma unroll
                         for (int w = 0; w < NW; w++)
 #pragma unroll
                             for (int p = 0; p < PV; p++) Vs[0][w][p] = V[w][p];
                         load_m(wrap_m(mslot0 + r - HALF), Ms[0]);  // centre row j + HALF
-                        finish_rows(std::integral_constant<int, 1>{}, Vs, Ms);
+                        const int pv = load_prev(0);
+                        finish_rows(std::integral_constant<int, 1>{}, Vs, Ms, &pv);
                     }
                 }
             }
@@ -526,31 +747,37 @@ __global__ void __launch_bounds__(32, WS<HALF, NW, SEG>::WARPS_PER_SM) k_bitslic
             slot0 = slot0 >= NR ? slot0 - NR : slot0;
             mslot0 += nrows;
             mslot0 = mslot0 >= NRM ? mslot0 - NRM : mslot0;
+            tslot = (tslot + nrows) % N;
         }
+    }
+
+    if constexpr (TM) {
+        tm_wait_st();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tring), "r"((uint32_t)C::TCOLS) : "memory");
     }
 }
 
-template <int HALF, int NW, int SEG, bool C2 = false>
+template <int HALF, int NW, int SEG, bool C2, bool TM>
 int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand, int max_cand)
 {
-    using C = WS<HALF, NW, SEG>;
+    using C = WS<HALF, NW, SEG, TM>;
     // MULTI: more than one chunk of 32*NW shifts, i.e. (best, web) are merged across passes
     const bool multi = !C2 && h.g.D > 32 * NW;
-    auto kern = C2 ? k_bitslice<HALF, NW, SEG, false, C2>
-                   : (multi ? k_bitslice<HALF, NW, SEG, true, false> : k_bitslice<HALF, NW, SEG, false, false>);
-    static int occ_cache[2][64] = {{0}};  // per instantiation, per MULTI flavour and per device
-    int dev = 0;
-    SM_CUDA(cudaGetDevice(&dev));
-    dev &= 63;
-    int *occ_of_device = occ_cache[multi ? 1 : 0];
-    if (occ_of_device[dev] == 0) {
-        SM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    auto kern = C2 ? k_bitslice<HALF, NW, SEG, false, C2, TM>
+                   : (multi ? k_bitslice<HALF, NW, SEG, true, false, TM> : k_bitslice<HALF, NW, SEG, false, false, TM>);
+    // the resident warps per SM of this instantiation on the current device: asked once per context
+    // (prepare_bitslice at sm_create, kept in HotArgs::blocks_per_sm), never cached in a static
+    int warps_per_sm = h.blocks_per_sm;
+    if (mode == MODE_PREPARE || warps_per_sm <= 0) {
+        SM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_REQ));
         int occ = 0;
-        SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, C::SMEM));
-        occ_of_device[dev] = occ > 0 ? occ : 1;
+        SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * C::WPC, C::SMEM_REQ));
+        warps_per_sm = (occ > 0 ? occ : 1) * C::WPC;
     }
-    if (mode == MODE_PREPARE) return 0;  // module loaded, attribute set, occupancy cached
-    const int blocks_per_sm = occ_of_device[dev];
+    if (mode == MODE_PREPARE) return warps_per_sm;  // module loaded, attribute set
     BitsliceArgs a;
     a.h = h;
     const int strip_cols = C2 ? C::TW * NW : C::TW;
@@ -573,7 +800,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *can
         const double f[] = {0.5, 0.625, 0.75, 0.875, 1.0, 1.25, 1.5, 2.0, 2.5, 3.0, 4.0};
         int n = 0;
         for (double x : f) {
-            int rows, sg = shape((int)(x * num_sms * blocks_per_sm / strips), rows);
+            int rows, sg = shape((int)(x * num_sms * warps_per_sm / strips), rows);
             bool seen = false;
             for (int k = 0; k < n; k++) seen |= cand[k] == sg;
             if (!seen && n < max_cand) cand[n++] = sg;
@@ -584,22 +811,21 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *can
     if (h.npairs == 1) {
         // latency mode (one pair): the shape timed best at sm_create (force_segs), else one full
         // wave of resident warps
-        segs = h.force_segs > 0 ? h.force_segs : num_sms * blocks_per_sm / strips;
+        segs = h.force_segs > 0 ? h.force_segs : num_sms * warps_per_sm / strips;
     } else {
-        // throughput mode (several pairs per launch): runs of about SMB_TR windows, whatever the
+        // throughput mode (several pairs per launch): runs of about 32 windows, whatever the
         // number of CTAs -- the launch may be several waves deep, the block scheduler keeps the
         // slots full and the next launch (other stream) covers the tail
-        static const int tr_env = getenv("SMB_TR") ? atoi(getenv("SMB_TR")) : 32;  // experiment hook
-        const int want = tr_env * C::N;
+        const int want = throughput_run_windows() * C::N;
         segs = (h.g.BH + want - 1) / want;
     }
     segs = shape(segs, a.rows_per_seg);
-    dim3 grid(strips, segs, h.npairs);
+    dim3 grid((strips + C::WPC - 1) / C::WPC, segs, h.npairs);
     if (h.after_pack) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
-        cfg.blockDim = dim3(32);
-        cfg.dynamicSmemBytes = C::SMEM;
+        cfg.blockDim = dim3(32 * C::WPC);
+        cfg.dynamicSmemBytes = C::SMEM_REQ;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -608,42 +834,73 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *can
         cfg.numAttrs = 1;
         SM_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     } else {
-        kern<<<grid, 32, C::SMEM, s>>>(a);
+        kern<<<grid, 32 * C::WPC, C::SMEM_REQ, s>>>(a);
     }
     SM_CUDA(cudaGetLastError());
     return 1;
 }
 
-// walker segment length: shorter walks = less shared memory (fewer rows per block) but more
-// warm-up steps per output.  Measured on config 2 (us per pair, batched): 8 -> 18.2, 16 -> 18.0,
-// 32 -> 25.2; on config 4: 16 -> 56, 32 -> 61.
-constexpr int seg_for(int half, int nw) { return 16; }
+// How a lane's words are used and how long a walker's segment is.
+//   words: two shift words of one pixel (64 shifts per pass); for num_shifts <= 32 the one shift word of two
+//          pixels (column pairs, C2) for windows up to 13 and frames at least one 64-column strip wide, else one
+//          word of one pixel.  Measured at 1080p, one pair per launch, 32 shifts: window 9: 19.4 vs 22.9 us,
+//          window 13: 22.9 vs 23.7, window 17: 25.8 vs 24.6.
+//   segment: shorter walks = fewer rows per block = smaller rings, but more window-filling steps per output.
+//          Measured on config 2 (us per pair, batched): 8 -> 18.2, 16 -> 18.0, 32 -> 25.2.
+struct Shape {
+    int nw, seg;
+    bool c2, tm;
+};
 
-template <int NW>
-int dispatch_half(int half, const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand = nullptr, int max_cand = 0)
+constexpr int C2_MAX_HALF = 6;
+
+static Shape pick_shape(const HotArgs &h)
 {
-    switch (half) {
-#define SM_CASE(HF) \
-    case HF: return launch_one<HF, NW, seg_for(HF, NW)>(h, num_sms, s, mode, cand, max_cand);
-        SM_CASE(0) SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5)
-        SM_CASE(6) SM_CASE(7) SM_CASE(8) SM_CASE(9) SM_CASE(10)
-        SM_CASE(11) SM_CASE(12) SM_CASE(13) SM_CASE(14) SM_CASE(15)
-#undef SM_CASE
-    default: set_error("bit-sliced kernel: window half %d not instantiated", half); return SM_ERR_ARG;
+    Shape sh;
+    sh.seg = 16;
+    sh.tm = false;
+    if (h.g.D > 32) {
+        sh.nw = 2;
+        sh.c2 = false;
+    } else {
+        sh.c2 = h.g.W >= 64 && h.g.half <= C2_MAX_HALF;
+        sh.nw = sh.c2 ? 2 : 1;
     }
+#ifdef SMB_DEV  // experiment hooks of the development build only (make DEV=1); never in the shipped library
+    if (getenv("SMB_NO_C2") && atoi(getenv("SMB_NO_C2")) && sh.c2) sh.c2 = false, sh.nw = 1;
+    if (getenv("SMB_NW") && !sh.c2) sh.nw = atoi(getenv("SMB_NW"));
+    if (getenv("SMB_SEG")) sh.seg = atoi(getenv("SMB_SEG"));
+    if (getenv("SMB_TM")) sh.tm = atoi(getenv("SMB_TM")) != 0;
+#endif
+    return sh;
 }
 
-// column pairs (C2): instantiated for the windows where it was measured faster than one word per lane
-constexpr int C2_MAX_HALF = 6;
-int dispatch_half_c2(int half, const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand, int max_cand)
+static int dispatch(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand = nullptr, int max_cand = 0)
 {
-    switch (half) {
-#define SM_CASE(HF) \
-    case HF: return launch_one<HF, 2, seg_for(HF, 2), true>(h, num_sms, s, mode, cand, max_cand);
-        SM_CASE(0) SM_CASE(1) SM_CASE(2) SM_CASE(3) SM_CASE(4) SM_CASE(5) SM_CASE(6)
-#undef SM_CASE
-    default: set_error("bit-sliced kernel: window half %d not instantiated for column pairs", half); return SM_ERR_ARG;
-    }
+    const Shape sh = pick_shape(h);
+    const int half = h.g.half;
+#define SM_SHAPE_TM(HF, NW_, SEG_, C2_, TM_) \
+    if (half == HF && sh.nw == NW_ && sh.seg == SEG_ && sh.c2 == C2_ && sh.tm == TM_) \
+        return launch_one<HF, NW_, SEG_, C2_, TM_>(h, num_sms, s, mode, cand, max_cand);
+#define SM_HALVES(M, ...) \
+    M(0, __VA_ARGS__) M(1, __VA_ARGS__) M(2, __VA_ARGS__) M(3, __VA_ARGS__) M(4, __VA_ARGS__) M(5, __VA_ARGS__) \
+    M(6, __VA_ARGS__) M(7, __VA_ARGS__) M(8, __VA_ARGS__) M(9, __VA_ARGS__) M(10, __VA_ARGS__) M(11, __VA_ARGS__) \
+    M(12, __VA_ARGS__) M(13, __VA_ARGS__) M(14, __VA_ARGS__) M(15, __VA_ARGS__)
+    SM_HALVES(SM_SHAPE_TM, 1, 16, false, false)
+    SM_HALVES(SM_SHAPE_TM, 2, 16, false, false)
+    SM_HALVES(SM_SHAPE_TM, 1, 16, false, true)
+    SM_HALVES(SM_SHAPE_TM, 2, 16, false, true)
+#define SM_C2(TM_) \
+    SM_SHAPE_TM(0, 2, 16, true, TM_) SM_SHAPE_TM(1, 2, 16, true, TM_) SM_SHAPE_TM(2, 2, 16, true, TM_) \
+    SM_SHAPE_TM(3, 2, 16, true, TM_) SM_SHAPE_TM(4, 2, 16, true, TM_) SM_SHAPE_TM(5, 2, 16, true, TM_) \
+    SM_SHAPE_TM(6, 2, 16, true, TM_)
+    SM_C2(false) SM_C2(true)
+#undef SM_C2
+#undef SM_HALVES
+#undef SM_SHAPE_TM
+    set_error("bit-sliced kernel: window half %d with %d word(s) per lane and %d-column walks is not instantiated",
+              half, sh.nw, sh.seg);
+    return SM_ERR_ARG;
 }
 
 }  // namespace
@@ -651,28 +908,6 @@ int dispatch_half_c2(int half, const HotArgs &h, int num_sms, cudaStream_t s, in
 // square_width up to 31 (the reference default is 21, stereo.c:8): 5 planes hold a row count of up to 31 and a
 // walk of 16 + 2*15 steps fits the walker's 96-bit window; wider windows take the direct kernel.
 bool bitslice_supports(int half, int D) { return half >= 0 && half <= 15 && D >= 1 && D <= 512; }
-
-// How a lane's words are used: two shift words of one pixel (64 shifts per pass; one word per pass with more
-// passes was measured slower: 87 vs 60 us on config 4); for num_shifts <= 32 the one shift word of two pixels
-// (column pairs, C2) for windows up to 13 and frames at least one 64-column strip wide, else one word of one
-// pixel.  Measured at 1080p, one pair per launch, 32 shifts: window 9: 19.4 vs 22.9 us, window 13: 22.9 vs 23.7,
-// window 17: 25.8 vs 24.6 (the two-word rings of wide windows leave 5 warps per SM against 8).
-enum { WORDS_ONE = 1, WORDS_TWO_SHIFT = 2, WORDS_TWO_COLUMNS = 3 };
-static int words_mode(const HotArgs &h)
-{
-    static const int no_c2 = getenv("SMB_NO_C2") ? atoi(getenv("SMB_NO_C2")) : 0;  // experiment hook
-    if (h.g.D > 32) return WORDS_TWO_SHIFT;
-    return (h.g.W >= 64 && h.g.half <= C2_MAX_HALF && !no_c2) ? WORDS_TWO_COLUMNS : WORDS_ONE;
-}
-
-static int dispatch(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand = nullptr, int max_cand = 0)
-{
-    switch (words_mode(h)) {
-    case WORDS_ONE: return dispatch_half<1>(h.g.half, h, num_sms, s, mode, cand, max_cand);
-    case WORDS_TWO_COLUMNS: return dispatch_half_c2(h.g.half, h, num_sms, s, mode, cand, max_cand);
-    default: return dispatch_half<2>(h.g.half, h, num_sms, s, mode, cand, max_cand);
-    }
-}
 
 int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s) { return dispatch(h, num_sms, s, MODE_LAUNCH); }
 
@@ -683,18 +918,17 @@ int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s) { return disp
 int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 {
     // enough pairs that one launch is a few waves of warps (about 8 resident per SM)
-    const int strip_cols = words_mode(h) == WORDS_TWO_COLUMNS ? 64 : 32;
+    const int strip_cols = pick_shape(h).c2 ? 64 : 32;
     const int N = 2 * h.g.half + 1, strips = (h.g.W + strip_cols - 1) / strip_cols;
-    static const int tr_env = getenv("SMB_TR") ? atoi(getenv("SMB_TR")) : 32;
-    const int want = tr_env * N;
+    const int want = throughput_run_windows() * N;
     const int segs = (h.g.BH + want - 1) / want > 0 ? (h.g.BH + want - 1) / want : 1;
     int p = 1;
     while (p < max_pairs && strips * segs * p < 3 * num_sms * 8) p++;
     return p;
 }
 
-// Loads the kernel this geometry will use, sets its shared-memory attribute and caches its
-// occupancy, so that the first sm_match_wta call pays none of that.
+// Loads the kernel this geometry will use and sets its shared-memory attribute, so that the first
+// sm_match_wta call pays none of that; returns its resident warps per SM (for HotArgs::blocks_per_sm).
 int prepare_bitslice(const HotArgs &h, int num_sms) { return dispatch(h, num_sms, nullptr, MODE_PREPARE); }
 
 // Launch shapes (number of row runs per strip) worth timing for a single-pair launch of this

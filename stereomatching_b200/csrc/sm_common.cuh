@@ -81,6 +81,8 @@ struct HotArgs {
     bool after_pack = false;
     // one pair per launch: number of row runs per strip (0 = one wave of resident warps)
     int force_segs = 0;
+    // resident warps per SM of the bit-sliced kernel this geometry uses (prepare_bitslice; 0 = ask)
+    int blocks_per_sm = 0;
 };
 
 // launchers (each returns the number of kernels launched, or a negative sm_status)

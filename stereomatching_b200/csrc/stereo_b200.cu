@@ -48,6 +48,7 @@ struct sm_ctx {
     int prof_cap = 0, prof_n = 0;
     int last_launches = 0;
     int tuned_segs = 0;  // single-pair launch shape of the bit-sliced kernel, timed at create (0: default)
+    int occ = 0;         // resident warps per SM of the bit-sliced kernel of this geometry (prepare_bitslice)
 
     // frame-sized device arrays (a band context touches only the rows it needs)
     uint8_t *img_u8[2] = {nullptr, nullptr};
@@ -206,6 +207,7 @@ HotArgs hot_args(sm_ctx *c, int32_t *best, int32_t *web)
     a.web = web;
     a.row0 = c->row0;
     a.force_segs = c->tuned_segs;
+    a.blocks_per_sm = c->occ;
     return a;
 }
 
@@ -234,7 +236,11 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
     launches += rc;
     if (pe) SM_CUDA(cudaEventRecord(pe[1], c->stream));
     HotArgs a = hot_args(c, best, web);
-    static const bool no_pdl = getenv("SMB_NO_PDL") && atoi(getenv("SMB_NO_PDL"));  // experiment hook
+#ifdef SMB_DEV
+    static const bool no_pdl = getenv("SMB_NO_PDL") && atoi(getenv("SMB_NO_PDL"));  // experiment hook, development build only
+#else
+    constexpr bool no_pdl = false;
+#endif
     a.after_pack = pe == nullptr && !no_pdl;  // nothing lies between the two launches unless the per-kernel profile is on
     rc = launch_main(c, a, c->stream);
     if (rc < 0) return rc;
@@ -421,6 +427,7 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
     if (bitslice_supports(c->half, c->D)) {
         HotArgs a = hot_args(c, c->best, c->web);
         if ((rc = prepare_bitslice(a, c->num_sms)) < 0) return fail(rc);
+        c->occ = rc;
         if (!(getenv("SMB_NO_TUNE") && atoi(getenv("SMB_NO_TUNE"))) && (rc = tune_launch_shape(c)) < 0) return fail(rc);
     }
     *out = c;
@@ -645,7 +652,10 @@ extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_f
         c->batch_group = 1;
         if (kk == SM_KERNEL_BITSLICE) {
             HotArgs a = hot_args(c, d_best, d_web);
-            const int pmax = getenv("SMB_PMAX") ? atoi(getenv("SMB_PMAX")) : 16;  // experiment hook
+            int pmax = 16;
+#ifdef SMB_DEV
+            if (getenv("SMB_PMAX")) pmax = atoi(getenv("SMB_PMAX"));  // experiment hook, development build only
+#endif
             c->batch_group = bitslice_pairs_per_launch(a, c->num_sms, pmax);
         }
         SM_CUDA(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
