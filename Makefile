@@ -15,11 +15,6 @@ CC      := gcc
 NVCC    := nvcc
 SM_ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(SM_ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall
-# make DEV=1 lib: development build with the experiment hooks (SMB_* environment variables) and extra
-# kernel instantiations compiled in; the shipped library has none of them
-ifeq ($(DEV),1)
-    NVFLAGS += -DSMB_DEV
-endif
 CFLAGS  := -Wall -Wextra -std=gnu11 -Wno-unused-parameter -Iinclude
 
 ifeq ($(build),debug)
@@ -37,11 +32,18 @@ endif
 
 CSRC   := stereomatching_b200/csrc
 LIB    := stereomatching_b200/libstereo_b200.so
-KOBJS  := $(patsubst %,$(CSRC)/build/%.o,stereo_b200 k_edges k_pack k_direct k_bitslice k_step3 k_peak)
+KOBJS  := $(patsubst %,$(CSRC)/build/%.o,stereo_b200 k_edges k_pack k_direct k_bitslice k_step3)
 
-all: lib $(outdir)/stereopar $(outdir)/stereopar-ghost $(outdir)/stereobatch host/libhostimage.so
+all: lib benchlib $(outdir)/stereopar $(outdir)/stereopar-ghost $(outdir)/stereobatch host/libhostimage.so
 
 lib: $(LIB)
+
+# measurement-only microbenchmarks (INT32 issue peak, host<->device copy peak) for bench.py: its own library,
+# nothing of it is in the product
+benchlib: benchlib/libsmb_peaks.so
+
+benchlib/libsmb_peaks.so: benchlib/peaks.cu
+	$(NVCC) -O3 -std=c++17 $(SM_ARCH) -lineinfo -Xcompiler -fPIC -shared $< -o $@
 
 $(CSRC)/build/%.o: $(CSRC)/%.cu $(CSRC)/sm_common.cuh include/stereo_b200.h
 	@mkdir -p $(CSRC)/build
@@ -49,6 +51,20 @@ $(CSRC)/build/%.o: $(CSRC)/%.cu $(CSRC)/sm_common.cuh include/stereo_b200.h
 
 $(LIB): $(KOBJS)
 	$(NVCC) $(SM_ARCH) -shared $(KOBJS) -o $@
+
+# make dev: the development build (libstereo_b200_dev.so) with the experiment hooks (SMB_* environment
+# variables, -DSMB_DEV) compiled in; the shipped library has none of them.  Select it with
+# STEREO_B200_LIB=.../libstereo_b200_dev.so (tools/exp_shapes.py).  DEVFLAGS adds further -D switches.
+DEVLIB   := stereomatching_b200/libstereo_b200_dev.so
+DEVKOBJS := $(patsubst $(CSRC)/build/%,$(CSRC)/build_dev/%,$(KOBJS))
+dev: $(DEVLIB)
+
+$(CSRC)/build_dev/%.o: $(CSRC)/%.cu $(CSRC)/sm_common.cuh include/stereo_b200.h
+	@mkdir -p $(CSRC)/build_dev
+	$(NVCC) $(NVFLAGS) -DSMB_DEV $(DEVFLAGS) -c $< -o $@
+
+$(DEVLIB): $(DEVKOBJS)
+	$(NVCC) $(SM_ARCH) -shared $(DEVKOBJS) -o $@
 
 $(outdir):
 	mkdir -p $(outdir)
@@ -76,6 +92,6 @@ oracle:
 	if [ -d /root/reference/src ]; then $(MAKE) -C oracle ref; fi
 
 clean:
-	-rm -rf debug timing release $(CSRC)/build $(LIB)
+	-rm -rf debug timing release $(CSRC)/build $(CSRC)/build_dev $(LIB) $(DEVLIB) benchlib/libsmb_peaks.so
 
-.PHONY: all lib oracle clean
+.PHONY: all lib dev benchlib oracle clean

@@ -230,6 +230,7 @@ def run_b200_arm(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
+    import benchlib
     import stereomatching_b200 as smb
 
     if not torch.cuda.is_available():
@@ -367,14 +368,14 @@ def run_b200_arm(a, rank, world, local_rank):
     e2e8_val = world * Be * W * H * D * e2e_steps / te8 / 1e6
     e2e8_ok = bool(np.array_equal(hweb8.array[0], hweb.array[0].astype(np.uint8)))
     # the link's own ceiling for those two calls: pinned host<->device copies, both directions at once
-    h2d_gbs, d2h_gbs = smb.measure_copy_peak(local_rank, 2)
+    h2d_gbs, d2h_gbs = benchlib.measure_copy_peak(local_rank, 2)
     # clocks: every sample taken between the start of the device-timed region and the end of the e2e one
     clocks = sampler.stop(tw0, time.perf_counter()) if sampler else None
 
     if rank == 0:
         # ---- roofline of the dominant kernel ------------------------------------------------
         main_s = main_ms * 1e-3 / max(n_iso, 1)
-        peaks = {m: smb.measure_int_peak(local_rank, i) for i, m in
+        peaks = {m: benchlib.measure_int_peak(local_rank, i) for i, m in
                  enumerate(["iadd3", "lop3", "iadd3+imad", "lop3+imad"])}
         peak = max(peaks.values())  # the dual-pipe issue ceiling: the hardest denominator
         mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

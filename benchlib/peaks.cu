@@ -1,4 +1,7 @@
-// k_peak.cu -- INT32 issue-rate microbenchmark: the roofline denominator of the hot path.
+// benchlib/peaks.cu -- measurement-only microbenchmarks (libsmb_peaks.so), loaded by bench.py and the sweep
+// scripts through ctypes.  NOT part of libstereo_b200.so and not declared in include/stereo_b200.h.
+//
+// INT32 issue-rate microbenchmark: the roofline denominator of the hot path.
 //
 // MEASURED_PEAKS.json carries HBM GB/s and bf16 TFLOP/s only; this path is bound by the
 // integer ALU issue rate, so bench.py measures that peak on the box with
@@ -9,11 +12,22 @@
 //   mode 2: IADD3 + IMAD     (alu + fma pipes together -- the dual-issue ceiling)
 //   mode 3: LOP3 + IMAD
 // Result: thread-instructions per second (one instruction = one "integer op").
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
 #include <string.h>
 
-#include "sm_common.cuh"
+namespace {
 
-namespace smb {
+#define PK_CUDA(call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            fprintf(stderr, "%s:%d: %s -> %s\n", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return -2;                                                                                 \
+        }                                                                                              \
+    } while (0)
+
 
 constexpr int PEAK_REGS = 8;
 constexpr int PEAK_UNROLL = 16;  // rounds per loop iteration; one round = PEAK_REGS instructions
@@ -48,37 +62,35 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, int iters, uint
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
-}  // namespace smb
+}  // namespace
 
-using namespace smb;
-
-extern "C" int sm_measure_int_peak(int device, int mode, double *gops_per_s)
+extern "C" int smb_measure_int_peak(int device, int mode, double *gops_per_s)
 {
-    SM_REQUIRE(gops_per_s && mode >= 0 && mode <= 3, "sm_measure_int_peak: bad arguments");
+    if (!gops_per_s || mode < 0 || mode > 3) return -1;
     int prev = -1;
     cudaGetDevice(&prev);
-    SM_CUDA(cudaSetDevice(device));
+    PK_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
-    SM_CUDA(cudaGetDeviceProperties(&prop, device));
+    PK_CUDA(cudaGetDeviceProperties(&prop, device));
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2000;
     uint32_t *out = nullptr;
-    SM_CUDA(cudaMalloc(&out, (size_t)blocks * threads * sizeof(uint32_t)));
+    PK_CUDA(cudaMalloc(&out, (size_t)blocks * threads * sizeof(uint32_t)));
     cudaEvent_t e0, e1;
-    SM_CUDA(cudaEventCreate(&e0));
-    SM_CUDA(cudaEventCreate(&e1));
+    PK_CUDA(cudaEventCreate(&e0));
+    PK_CUDA(cudaEventCreate(&e1));
     float best_ms = 1e30f;
     for (int rep = 0; rep < 5; rep++) {  // rep 0 is the warm-up
-        SM_CUDA(cudaEventRecord(e0));
+        PK_CUDA(cudaEventRecord(e0));
         switch (mode) {
         case 0: k_int_peak<0><<<blocks, threads>>>(out, iters, 17u + rep); break;
         case 1: k_int_peak<1><<<blocks, threads>>>(out, iters, 17u + rep); break;
         case 2: k_int_peak<2><<<blocks, threads>>>(out, iters, 17u + rep); break;
         default: k_int_peak<3><<<blocks, threads>>>(out, iters, 17u + rep); break;
         }
-        SM_CUDA(cudaEventRecord(e1));
-        SM_CUDA(cudaEventSynchronize(e1));
+        PK_CUDA(cudaEventRecord(e1));
+        PK_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
-        SM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        PK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (rep > 0 && ms < best_ms) best_ms = ms;
     }
     double instr = (double)blocks * threads * iters * PEAK_UNROLL * PEAK_REGS;
@@ -87,46 +99,46 @@ extern "C" int sm_measure_int_peak(int device, int mode, double *gops_per_s)
     cudaEventDestroy(e1);
     cudaFree(out);
     if (prev >= 0) cudaSetDevice(prev);
-    return SM_OK;
+    return 0;
 }
 
 // Host <-> device copy bandwidth of this GPU's link from pinned memory: the ceiling of the
 // end-to-end (host buffers) figure.  mode 0: H2D alone, 1: D2H alone, 2: both directions at
 // once (two streams), reported per direction (H2D in gbs[0], D2H in gbs[1]).
-extern "C" int sm_measure_copy_peak(int device, int mode, double *gbs)
+extern "C" int smb_measure_copy_peak(int device, int mode, double *gbs)
 {
-    SM_REQUIRE(gbs && mode >= 0 && mode <= 2, "sm_measure_copy_peak: bad arguments");
+    if (!gbs || mode < 0 || mode > 2) return -1;
     int prev = -1;
     cudaGetDevice(&prev);
-    SM_CUDA(cudaSetDevice(device));
+    PK_CUDA(cudaSetDevice(device));
     const size_t bytes = (size_t)256 << 20;
     void *h[2] = {nullptr, nullptr}, *d[2] = {nullptr, nullptr};
     cudaStream_t st[2];
     cudaEvent_t e0[2], e1[2];
     for (int k = 0; k < 2; k++) {
-        SM_CUDA(cudaHostAlloc(&h[k], bytes, cudaHostAllocDefault));
+        PK_CUDA(cudaHostAlloc(&h[k], bytes, cudaHostAllocDefault));
         memset(h[k], k + 1, bytes);
-        SM_CUDA(cudaMalloc(&d[k], bytes));
-        SM_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
-        SM_CUDA(cudaEventCreate(&e0[k]));
-        SM_CUDA(cudaEventCreate(&e1[k]));
+        PK_CUDA(cudaMalloc(&d[k], bytes));
+        PK_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
+        PK_CUDA(cudaEventCreate(&e0[k]));
+        PK_CUDA(cudaEventCreate(&e1[k]));
     }
     gbs[0] = gbs[1] = 0.0;
     for (int rep = 0; rep < 4; rep++) {  // rep 0 is the warm-up
         for (int k = 0; k < 2; k++) {
             if (mode != 2 && k != mode) continue;
-            SM_CUDA(cudaEventRecord(e0[k], st[k]));
+            PK_CUDA(cudaEventRecord(e0[k], st[k]));
             if (k == 0)
-                SM_CUDA(cudaMemcpyAsync(d[0], h[0], bytes, cudaMemcpyHostToDevice, st[0]));
+                PK_CUDA(cudaMemcpyAsync(d[0], h[0], bytes, cudaMemcpyHostToDevice, st[0]));
             else
-                SM_CUDA(cudaMemcpyAsync(h[1], d[1], bytes, cudaMemcpyDeviceToHost, st[1]));
-            SM_CUDA(cudaEventRecord(e1[k], st[k]));
+                PK_CUDA(cudaMemcpyAsync(h[1], d[1], bytes, cudaMemcpyDeviceToHost, st[1]));
+            PK_CUDA(cudaEventRecord(e1[k], st[k]));
         }
         for (int k = 0; k < 2; k++) {
             if (mode != 2 && k != mode) continue;
-            SM_CUDA(cudaEventSynchronize(e1[k]));
+            PK_CUDA(cudaEventSynchronize(e1[k]));
             float ms = 0;
-            SM_CUDA(cudaEventElapsedTime(&ms, e0[k], e1[k]));
+            PK_CUDA(cudaEventElapsedTime(&ms, e0[k], e1[k]));
             const double g = (double)bytes / (ms * 1e-3) / 1e9;
             if (rep > 0 && g > gbs[k]) gbs[k] = g;
         }
@@ -139,5 +151,5 @@ extern "C" int sm_measure_copy_peak(int device, int mode, double *gbs)
         cudaFreeHost(h[k]);
     }
     if (prev >= 0) cudaSetDevice(prev);
-    return SM_OK;
+    return 0;
 }

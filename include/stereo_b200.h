@@ -73,6 +73,16 @@ typedef enum sm_kernel {
     SM_KERNEL_BITSLICE = 2 /* bit-sliced running box sums, 32 shifts per word (the fast path) */
 } sm_kernel;
 
+/* Context options (sm_set_option): what used to be environment hooks. */
+typedef enum sm_option {
+    SM_OPT_EDGES_FP64 = 1, /* 1: always run the FP64 edge detector (the reference's arithmetic, stereo.cu:83-92),
+                              even for 8-bit uploads; 0 (default): the integer table path for 8-bit images */
+    SM_OPT_PIPE_GROUP = 2, /* pairs per stage of the sm_run_batch pipeline; 0 (default): chosen by frame size.
+                              Only before the first sm_run_batch of the context */
+    SM_OPT_ROW_RUNS = 3    /* row runs per 32-column strip of a one-pair launch of the bit-sliced kernel;
+                              0 (default): the kernel's cost model */
+} sm_option;
+
 /* ---- library-level -------------------------------------------------------- */
 
 /* Message of the last failure on this thread ("" if none). */
@@ -112,6 +122,7 @@ int sm_destroy(sm_ctx *ctx);
 /* Use an existing cudaStream_t (passed as void*) instead of the context's own. */
 int sm_set_stream(sm_ctx *ctx, void *cuda_stream);
 int sm_set_kernel(sm_ctx *ctx, int kernel);
+int sm_set_option(sm_ctx *ctx, int option, int value);
 int sm_synchronize(sm_ctx *ctx);
 
 /* ---- step 0: upload ------------------------------------------------------- */
@@ -176,15 +187,6 @@ int sm_last_launches(sm_ctx *ctx);
  * off. */
 int sm_profile_begin(sm_ctx *ctx, int max_calls);
 int sm_profile_read(sm_ctx *ctx, int *n_calls, double *pack_ms_total, double *main_ms_total);
-
-/* INT32 issue-rate microbenchmark (the roofline denominator of this path, which
- * MEASURED_PEAKS.json does not carry): mode 0 IADD3, 1 LOP3, 2 IADD3+IMAD, 3 LOP3+IMAD.
- * Result in 1e9 thread-instructions per second. */
-int sm_measure_int_peak(int device, int mode, double *gops_per_s);
-/* Pinned host <-> device copy bandwidth of the GPU's link, the ceiling of every figure
- * measured with host buffers (sm_run_batch): mode 0 H2D alone, 1 D2H alone, 2 both
- * directions at once.  gbs[0] = H2D GB/s, gbs[1] = D2H GB/s (0 for a direction not run). */
-int sm_measure_copy_peak(int device, int mode, double *gbs);
 
 /* ---- step 3 --------------------------------------------------- */
 

@@ -12,10 +12,11 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libstereo_b200.so")
+LIB_PATH = os.environ.get("STEREO_B200_LIB") or os.path.join(HERE, "libstereo_b200.so")
 
 WRAP, GHOST = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_BITSLICE = 0, 1, 2
+OPT_EDGES_FP64, OPT_PIPE_GROUP, OPT_ROW_RUNS = 1, 2, 3
 (EDGES1, EDGES2, MATCH, SCORE_ALL, SCORE, BEST, WEB, WEB_FILLED, OUTPUT) = range(9)
 _PLANE_DTYPE = {EDGES1: np.uint8, EDGES2: np.uint8, MATCH: np.uint8, SCORE_ALL: np.int32,
                 SCORE: np.int32, BEST: np.int32, WEB: np.int32, WEB_FILLED: np.int32,
@@ -28,7 +29,7 @@ SYMBOLS = [
     "sm_create", "sm_create_band", "sm_destroy", "sm_set_stream", "sm_set_kernel",
     "sm_synchronize", "sm_upload_f64", "sm_upload_u8", "sm_edges", "sm_set_edges",
     "sm_match_wta", "sm_match_wta_dev", "sm_match_wta_dev_batch", "sm_elapsed_ms", "sm_last_launches",
-    "sm_profile_begin", "sm_profile_read", "sm_measure_int_peak", "sm_measure_copy_peak",
+    "sm_profile_begin", "sm_profile_read", "sm_set_option",
     "sm_fill_web_holes", "sm_set_web", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
     "sm_run_batch", "sm_band_rows",
     "sm_multi_create", "sm_multi_run_batch", "sm_multi_device_count", "sm_multi_destroy",
@@ -61,6 +62,7 @@ def lib() -> C.CDLL:
         L.sm_destroy.argtypes = [vp]
         L.sm_set_stream.argtypes = [vp, vp]
         L.sm_set_kernel.argtypes = [vp, i]
+        L.sm_set_option.argtypes = [vp, i, i]
         L.sm_synchronize.argtypes = [vp]
         L.sm_upload_f64.argtypes = [vp, vp, vp]
         L.sm_upload_u8.argtypes = [vp, vp, vp]
@@ -73,8 +75,6 @@ def lib() -> C.CDLL:
         L.sm_last_launches.argtypes = [vp]
         L.sm_profile_begin.argtypes = [vp, i]
         L.sm_profile_read.argtypes = [vp, C.POINTER(i), C.POINTER(d), C.POINTER(d)]
-        L.sm_measure_int_peak.argtypes = [i, i, C.POINTER(d)]
-        L.sm_measure_copy_peak.argtypes = [i, i, C.POINTER(d)]
         L.sm_fill_web_holes.argtypes = [vp, i]
         L.sm_set_web.argtypes = [vp, vp]
         L.sm_draw_contour_map.argtypes = [vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -101,20 +101,6 @@ def _check(rc: int) -> int:
 
 def device_count() -> int:
     return _check(lib().sm_device_count())
-
-
-def measure_int_peak(device: int = 0, mode: int = 2) -> float:
-    """INT32 issue rate in 1e9 thread-instructions/s (0 IADD3, 1 LOP3, 2 IADD3+IMAD, 3 LOP3+IMAD)."""
-    g = C.c_double()
-    _check(lib().sm_measure_int_peak(device, mode, C.byref(g)))
-    return g.value
-
-
-def measure_copy_peak(device: int = 0, mode: int = 2):
-    """Pinned host<->device copy bandwidth in GB/s as (h2d, d2h); mode 0 H2D alone, 1 D2H alone, 2 both at once."""
-    g = (C.c_double * 2)()
-    _check(lib().sm_measure_copy_peak(device, mode, g))
-    return g[0], g[1]
 
 
 def band_rows(height: int, n_bands: int, band: int):
@@ -184,6 +170,9 @@ class StereoContext:
     # -- configuration -------------------------------------------------------
     def set_kernel(self, kernel):
         _check(lib().sm_set_kernel(self._c, kernel))
+
+    def set_option(self, option, value):
+        _check(lib().sm_set_option(self._c, option, int(value)))
 
     def set_stream(self, cuda_stream: int):
         _check(lib().sm_set_stream(self._c, C.c_void_p(cuda_stream)))

@@ -25,21 +25,31 @@
 //        "all shifts", giving web = num_shifts as the reference does.
 //
 // Decomposition.  ONE WARP owns a strip of 32 pixel columns and a run of output rows and is
-// fully autonomous (one warp per CTA, only __syncwarp): it streams down its rows in blocks
-// of RB rows.  Per block: pass A with the 32 lanes as walkers (lane -> segment, row, shift
-// word; every walker reads its own windows of the packed rows straight from global memory,
-// prefetched one block ahead; the first 2*half words of a walk are summed by a carry-save
-// tree, csa_planes), H rows and centre match words into two small shared-memory rings, then
-// pass B with the 32 lanes as pixel columns.  The H ring keeps RB + 2*half + 1 rows so the row
-// leaving the vertical window is still there.  More than 32*NW shifts are processed as
-// successive chunks over the same rows, merging (best, web) in place (a later chunk holds
-// higher shifts, so it wins ties).  With 32 shifts or fewer the two words of a lane are two
-// pixels instead (C2, 64-column strips).
+// fully autonomous (only __syncwarp while it works): it streams down its rows in blocks of RB
+// rows.  Per block: pass A with the 32 lanes as walkers (lane -> segment, row, shift word; every
+// walker reads its own windows of the packed rows straight from global memory, prefetched one
+// block ahead; the first 2*half words of a walk are summed by a carry-save tree, csa_planes),
+// the block's H rows and centre match words through shared memory (the walker -> column
+// transposition), then pass B with the 32 lanes as pixel columns.
+//
+// The vertical window lives in TENSOR MEMORY.  Pass B needs, 2*half+1 rows later, the H planes
+// of the row that leaves the window.  A lane only ever re-reads what IT stored, which is exactly
+// the access pattern of tcgen05.ld/st.32x32b (thread i <-> TMEM lane i): every warp keeps a ring
+// of 2*half+1 rows x NW*KH columns in its own 32 TMEM lanes, reads the leaving row back from it
+// and writes the entering row over it.  Shared memory then holds one block of rows instead of a
+// ring of RB + 2*half + 1 (43 KB per warp at window 21, 5 warps per SM; now 15.6 KB and 8 warps,
+// bounded by the 512 TMEM columns).  A warp reaches only TMEM lanes 32*(warp%4)..+31, hence FOUR
+// warps (four adjacent strips) per CTA and one allocation per CTA; the warps share nothing else.
+//
+// More than 32*NW shifts are processed as successive chunks over the same rows, merging (best,
+// web) in place (a later chunk holds higher shifts, so it wins ties; the earlier chunks' best of
+// a block's rows is prefetched before pass A).  With 32 shifts or fewer the two words of a lane
+// are two pixels instead (C2, 64-column strips).
 //
 // Launching.  Several pairs per launch (grid z) run in the throughput shape: runs of about 32
-// windows, several waves deep.  One pair per launch runs in the shape sm_create timed fastest
-// for the geometry (HotArgs::force_segs, bitslice_seg_candidates), as the programmatic
-// dependent of the pack kernel (griddepcontrol.wait below).  DESIGN.md 4.1 has the numbers.
+// windows, several waves deep.  One pair per launch takes the number of row runs a small cost
+// model picks (launch_one), as the programmatic dependent of the pack kernel
+// (griddepcontrol.wait below).  DESIGN.md 4.1 has the numbers.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -64,14 +74,7 @@ __host__ __device__ constexpr int pow2_at_least(int v)
     return p;
 }
 
-// TM: the rows of the vertical window live in TENSOR MEMORY (the 256 KB per SM that tcgen05 normally uses for MMA
-// accumulators), not in shared memory.  A lane of pass B only ever re-reads what IT stored 2*half+1 rows earlier,
-// which is exactly the access pattern of tcgen05.ld/st.32x32b (thread i <-> TMEM lane i): the leaving row's
-// H planes are read back from the lane's own TMEM columns and the entering row's are written over them.  Shared memory
-// then holds only the RB rows of a block (the walker -> column transposition) and the centre-match ring, which
-// is what lifts the 5-plane windows (17..21) from 5 to 8 warps per SM.  A warp reaches only TMEM lanes
-// 32*(warp%4)..+31, hence four warps (four strips) per CTA, one allocation per CTA.
-template <int HALF, int NW, int SEG, bool TM = false>
+template <int HALF, int NW, int SEG>
 struct WS {
     static constexpr int N = 2 * HALF + 1;       // window side
     static constexpr int KH = bits_for(N);       // planes of a horizontal count (<= N)
@@ -79,7 +82,7 @@ struct WS {
     static constexpr int TW = 32;                // pixel columns per warp
     static constexpr int NSEG = TW / SEG;        // walkers per (row, word)
     static constexpr int RB = 32 / (NW * NSEG);  // rows per block: 32 walkers
-    static constexpr int NR = TM ? RB : RB + N;  // H rows in shared memory: the block (TM) or the ring
+    static constexpr int NR = RB;                // H rows in shared memory: one block
     static constexpr int NRM = RB + HALF + 1;    // centre-match ring rows
     static constexpr int HROW = TW + 1;          // uint4 per (ring row, word); +1 staggers banks
     // words per M ring row, +stagger; two words per lane: even, so that the LDS.64 stays aligned
@@ -88,27 +91,25 @@ struct WS {
     static constexpr int H5N = KH > 4 ? ((NR * NW * HROW + 3) & ~3) : 0;  // words, 16-byte multiple
     static constexpr int MQN = (NRM * MROW + 3) & ~3;                     // words, 16-byte multiple
     static constexpr size_t SMEM = (size_t)NR * NW * HROW * 16 + (size_t)H5N * 4 + (size_t)MQN * 4;  // per warp
-    static constexpr int WPC = TM ? 4 : 1;                                // warps per CTA
-    static constexpr size_t SMEM_CTA = WPC * SMEM + (TM ? 16 : 0);        // + the TMEM base address slot
+    static constexpr int WPC = 4;                                         // warps per CTA (TMEM lane quarters)
+    static constexpr size_t SMEM_CTA = WPC * SMEM + 16;                   // + the TMEM base address slot
     static constexpr int EC = NW * KH;                                    // TMEM columns per ring row
     static constexpr int TCOLS = pow2_at_least(N * EC);                   // allocation: a power of two >= 32
     static constexpr int CTAS_SMEM = (int)((227 * 1024) / (SMEM_CTA + 1024));
-    static constexpr int CTAS_TMEM = TM ? 512 / TCOLS : 64;
+    static constexpr int CTAS_TMEM = 512 / TCOLS;
+    // 16 warps per SM at most (measured: 12 and 16 run alike, and 16 x 128 registers is where ptxas stops spilling)
     static constexpr int CTAS_PER_SM_ = CTAS_SMEM < CTAS_TMEM ? CTAS_SMEM : CTAS_TMEM;
-    static constexpr int CTAS_PER_SM = CTAS_PER_SM_ * WPC > 32 ? 32 / WPC : (CTAS_PER_SM_ < 1 ? 1 : CTAS_PER_SM_);
-    // warps per SM that shared memory (and TMEM) allow: ptxas is told, so that it spends the
-    // registers this occupancy leaves free on interleaving independent rows
-    static constexpr int WARPS_PER_SM = CTAS_PER_SM * WPC;
+    static constexpr int CTAS_PER_SM = CTAS_PER_SM_ > 4 ? 4 : (CTAS_PER_SM_ < 1 ? 1 : CTAS_PER_SM_);
     // dynamic shared memory to ask for: never more co-resident CTAs than TMEM allocations fit (a CTA that cannot
     // allocate would sit on its shared memory and registers, spinning in tcgen05.alloc)
-    static constexpr size_t SMEM_REQ = !TM ? SMEM_CTA
-        : (SMEM_CTA > (size_t)(227 * 1024) / (CTAS_PER_SM + 1) ? SMEM_CTA : (size_t)(227 * 1024) / (CTAS_PER_SM + 1) + 16);
+    static constexpr size_t SMEM_REQ =
+        SMEM_CTA > (size_t)(227 * 1024) / (CTAS_PER_SM + 1) ? SMEM_CTA : (size_t)(227 * 1024) / (CTAS_PER_SM + 1) + 16;
     static_assert(RB >= 1 && RB * NW * NSEG == 32, "walkers must fill the warp");
     static_assert(STEPS + 32 <= 96 && STEPS < 64, "walker windows: 96 bits of RB, 64 bits of LA/LB");
-    static_assert(!TM || N * EC <= 512, "the vertical window must fit one TMEM allocation");
+    static_assert(N * EC <= 512, "the vertical window must fit one TMEM allocation");
 };
 
-enum { MODE_LAUNCH = 0, MODE_PREPARE = 1, MODE_CANDIDATES = 2 };
+enum { MODE_LAUNCH = 0, MODE_PREPARE = 1 };
 
 // throughput mode (several pairs per launch): a warp's run of rows, in windows
 inline int throughput_run_windows()
@@ -318,11 +319,11 @@ __device__ __forceinline__ void csa_planes(const uint32_t (&a)[N], uint32_t (&P)
 // WRAP mode and away from the borders in GHOST mode), so the validity select drops out.
 // The first 2*HALF match words only fill the window: they are summed by a carry-save tree
 // instead of 2*HALF counter steps; from then on one word enters and one leaves per step.
-template <int HALF, int NW, int SEG, bool VALID_ALL, bool TM>
+template <int HALF, int NW, int SEG, bool VALID_ALL>
 __device__ __forceinline__ void walk(const uint32_t (&q)[3], const uint32_t (&lw)[2], const uint32_t (&vw)[2],
                                      uint4 *hq, uint32_t *h5, uint32_t *mq)
 {
-    using C = WS<HALF, NW, SEG, TM>;
+    using C = WS<HALF, NW, SEG>;
     constexpr int N = C::N, KH = C::KH, STEPS = C::STEPS;
     uint32_t P[5] = {0, 0, 0, 0, 0};
     uint32_t m[STEPS];
@@ -418,26 +419,26 @@ __device__ __forceinline__ void store_if(int32_t *p, int v, bool on)
 // two-word machinery unchanged; only the column of word w, the shift base and the winner-take-all (one per word)
 // differ.  It runs 32-shift problems at the per-word cost of the two-word kernel (8-row blocks, 17-row rings at
 // window 9) instead of the one-word kernel's 16-row blocks.
-template <int HALF, int NW, int SEG, bool MULTI, bool C2, bool TM>
-__global__ void __launch_bounds__(32 * WS<HALF, NW, SEG, TM>::WPC, WS<HALF, NW, SEG, TM>::CTAS_PER_SM)
+template <int HALF, int NW, int SEG, bool MULTI, bool C2>
+__global__ void __launch_bounds__(32 * WS<HALF, NW, SEG>::WPC, WS<HALF, NW, SEG>::CTAS_PER_SM)
 k_bitslice(BitsliceArgs a)
 {
-    using C = WS<HALF, NW, SEG, TM>;
+    using C = WS<HALF, NW, SEG>;
     constexpr int N = C::N, KH = C::KH, PV = C::PV, TW = C::TW, RB = C::RB, NR = C::NR, NRM = C::NRM;
     constexpr int HROW = C::HROW, MROW = C::MROW, STEPS = C::STEPS, EC = C::EC, WPC = C::WPC;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = TM ? (int)(threadIdx.x >> 5) : 0;  // one strip per warp; the warps of a CTA share nothing but
-    const int lane = threadIdx.x & 31;                  // the TMEM allocation
-    unsigned char *smem_w = smem_raw + (TM ? 16 : 0) + (size_t)warp * C::SMEM;
+    const int warp = (int)(threadIdx.x >> 5);  // one strip per warp; the warps of a CTA share nothing but
+    const int lane = threadIdx.x & 31;         // the TMEM allocation
+    unsigned char *smem_w = smem_raw + 16 + (size_t)warp * C::SMEM;
     uint4 *Hq = reinterpret_cast<uint4 *>(smem_w);                     // [NR][NW][HROW]
     uint32_t *H5 = reinterpret_cast<uint32_t *>(Hq + NR * NW * HROW);  // [NR][NW][HROW] (KH == 5)
     uint32_t *Mq = H5 + C::H5N;                                        // [NRM][MROW], word (x, w) at x*NW + w
 
-    // TM: one TMEM allocation per CTA (warp 0 allocates, everybody reads the address after a barrier);
+    // one TMEM allocation per CTA (warp 0 allocates, everybody reads the address after a barrier);
     // this warp's ring row s is columns [s*EC, (s+1)*EC) of its own 32 lanes
     uint32_t tring = 0;
-    if constexpr (TM) {
+    {
         uint32_t *slot = reinterpret_cast<uint32_t *>(smem_raw);
         if (warp == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -480,7 +481,7 @@ k_bitslice(BitsliceArgs a)
         h[0] = qv.x, h[1] = qv.y, h[2] = qv.z, h[3] = qv.w;
         h[4] = KH > 4 ? H5[(slot * NW + w) * HROW + lane] : 0u;
     };
-    // TM: the KH planes of both words of a ring row <-> EC consecutive TMEM columns
+    // the KH planes of both words of a ring row <-> EC consecutive TMEM columns
     auto to_cols = [&](const uint32_t (&h)[NW][5], uint32_t (&e)[EC]) {
 #pragma unroll
         for (int w = 0; w < NW; w++)
@@ -516,25 +517,21 @@ k_bitslice(BitsliceArgs a)
         for (int w = 0; w < NW; w++) {
 #pragma unroll
             for (int p = 0; p < PV; p++) V[w][p] = 0;
-            // ring slot NR-1 (TM: N-1) stands for padded row ja-1: all zero, so that the first output row
-            // may subtract it like any other
-            if constexpr (!TM) {
-                Hq[((NR - 1) * NW + w) * HROW + lane] = make_uint4(0, 0, 0, 0);
-                if (KH > 4) H5[((NR - 1) * NW + w) * HROW + lane] = 0u;
-            }
         }
-        if constexpr (TM) {
+        {
+            // ring row N-1 stands for padded row ja-1: all zero, so that the first output row may subtract it
+            // like any other
             uint32_t z[EC];
 #pragma unroll
             for (int k = 0; k < EC; k++) z[k] = 0u;
             tm_wait_st();  // (the previous chunk's last rows)
             tm_store<EC>(tring + (N - 1) * EC, z);
         }
-        int tslot = 0;  // TM: ring row of padded row p0 (= (p0 - ja) mod N)
+        int tslot = 0;  // ring row of padded row p0 (= (p0 - ja) mod N)
 
         WalkRaw in = {};
         if (ja + wr < last_pr) load_walk_raw(in, a.h, ja + wr, rbit, lbit);
-        int slot0 = 0, mslot0 = 0;  // ring slots of padded row p0
+        int mslot0 = 0;  // centre-match ring slot of padded row p0
         // next output row, as a 32-bit element offset (frames are < 2^31 pixels): the address
         // arithmetic then is one multiply-add per store (FMA pipe) instead of 64-bit pointer adds
         int oidx = (a.h.row0 + ja) * g.W + ximg;
@@ -595,9 +592,8 @@ k_bitslice(BitsliceArgs a)
         };
         // ring index helpers: x in [0, 2n) -> x mod n, and x in [-n, n) -> x mod n, as one add + one unsigned min
         auto wrap_hi = [](int x, int n) { return (int)min((unsigned)x, (unsigned)(x - n)); };
-        auto wrap_lo = [](int x, int n) { return (int)min((unsigned)x, (unsigned)(x + n)); };
         auto wrap_m = [&](int ms) { return ms < 0 ? ms + NRM : (ms >= NRM ? ms - NRM : ms); };
-        // TM ring row of x = tslot + r, tslot < N, r < RB
+        // ring row of x = tslot + r, tslot < N, r < RB
         auto wrap_t = [&](int x) { return N >= RB ? wrap_hi(x, N) : x % N; };
 
         for (int p0 = ja; p0 < last_pr; p0 += RB) {
@@ -613,8 +609,7 @@ k_bitslice(BitsliceArgs a)
             // ---------------- pass A: 32 walkers ----------------
             {
                 const bool active = wr < nrows;
-                int slot = TM ? wr : slot0 + wr;
-                slot = slot >= NR ? slot - NR : slot;
+                const int slot = wr;
                 int mslot = mslot0 + wr;
                 mslot = mslot >= NRM ? mslot - NRM : mslot;
                 uint4 *hq = Hq + (slot * NW + ww) * HROW + ws * SEG;
@@ -629,9 +624,9 @@ k_bitslice(BitsliceArgs a)
                 const unsigned long long vl = (((unsigned long long)vw[1]) << 32) | vw[0];
                 const bool all_valid = (~vl & ((1ull << STEPS) - 1ull)) == 0ull;
                 if (__all_sync(0xFFFFFFFFu, all_valid || !active)) {
-                    if (active) walk<HALF, NW, SEG, true, TM>(q, lw, vw, hq, h5, mq);
+                    if (active) walk<HALF, NW, SEG, true>(q, lw, vw, hq, h5, mq);
                 } else {
-                    if (active) walk<HALF, NW, SEG, false, TM>(q, lw, vw, hq, h5, mq);
+                    if (active) walk<HALF, NW, SEG, false>(q, lw, vw, hq, h5, mq);
                 }
             }
             __syncwarp();
@@ -644,13 +639,13 @@ k_bitslice(BitsliceArgs a)
                 // steady state, branch-free: every row enters, one leaves, one output row.
                 // Rows go in groups of G so that their winner-take-all chains interleave.
                 constexpr int G = (RB % 4 == 0) ? 4 : ((RB % 2 == 0) ? 2 : 1);
-                constexpr int GT = TM && N < G ? 1 : G;  // TM: a group's rows must be distinct ring rows
+                constexpr int GT = N < G ? 1 : G;  // a group's rows must be distinct ring rows
 #pragma unroll
                 for (int r = 0; r < RB; r += G) {
                     uint32_t Vs[G][NW][PV], Ms[G][NW];
-                    uint32_t eo[G][EC];  // TM: the leaving rows, as read back from tensor memory
+                    uint32_t eo[G][EC];  // the leaving rows, as read back from tensor memory
                     int ts[G];
-                    if constexpr (TM) {
+                    {
 #pragma unroll
                         for (int k = 0; k < G; k++) ts[k] = wrap_t(tslot + r + k);
                         if (GT == G) {
@@ -665,28 +660,18 @@ k_bitslice(BitsliceArgs a)
 #pragma unroll
                     for (int k = 0; k < G; k++) {
                         uint32_t hn[NW][5], ho[NW][5];
-                        if constexpr (TM) {
-                            if (GT != G) {
-                                tm_wait_st();
-                                tm_load<EC>(tring + ts[k] * EC, eo[k]);
-                                tm_wait_ld();
-                                tm_pin<EC>(eo[k]);
-                            }
-                            from_cols(eo[k], ho);
-#pragma unroll
-                            for (int w = 0; w < NW; w++) load_h(r + k, w, hn[w]);
-                            uint32_t en[EC];
-                            to_cols(hn, en);
-                            tm_store<EC>(tring + ts[k] * EC, en);  // the entering row takes the leaving row's place
-                        } else {
-                            const int slot_n = wrap_hi(slot0 + r + k, NR);
-                            const int slot_o = wrap_lo(slot_n - N, NR);
-#pragma unroll
-                            for (int w = 0; w < NW; w++) {
-                                load_h(slot_n, w, hn[w]);
-                                load_h(slot_o, w, ho[w]);
-                            }
+                        if (GT != G) {
+                            tm_wait_st();
+                            tm_load<EC>(tring + ts[k] * EC, eo[k]);
+                            tm_wait_ld();
+                            tm_pin<EC>(eo[k]);
                         }
+                        from_cols(eo[k], ho);
+#pragma unroll
+                        for (int w = 0; w < NW; w++) load_h(r + k, w, hn[w]);
+                        uint32_t en[EC];
+                        to_cols(hn, en);
+                        tm_store<EC>(tring + ts[k] * EC, en);  // the entering row takes the leaving row's place
 #pragma unroll
                         for (int w = 0; w < NW; w++) {
                             planes_addsub<PV, KH>(V[w], hn[w], ho[w]);
@@ -700,13 +685,11 @@ k_bitslice(BitsliceArgs a)
             } else {
                 // warm-up rows (window still filling) and the ragged last block
                 for (int r = 0; r < nrows; r++) {
-                    int slot_n = TM ? r : slot0 + r;
-                    slot_n = slot_n >= NR ? slot_n - NR : slot_n;
                     const int pr = p0 + r;
                     uint32_t hn[NW][5], ho[NW][5];
 #pragma unroll
-                    for (int w = 0; w < NW; w++) load_h(slot_n, w, hn[w]);
-                    if constexpr (TM) {
+                    for (int w = 0; w < NW; w++) load_h(r, w, hn[w]);
+                    {
                         const int t = wrap_t(tslot + r);
                         if (pr > first_out) {  // padded row pr - N left the window: it is what ring row t holds
                             uint32_t eo[EC];
@@ -719,11 +702,6 @@ k_bitslice(BitsliceArgs a)
                         uint32_t en[EC];
                         to_cols(hn, en);
                         tm_store<EC>(tring + t * EC, en);
-                    } else if (pr > first_out) {
-                        int slot_o = slot_n - N;
-                        slot_o = slot_o < 0 ? slot_o + NR : slot_o;
-#pragma unroll
-                        for (int w = 0; w < NW; w++) load_h(slot_o, w, ho[w]);
                     }
 #pragma unroll
                     for (int w = 0; w < NW; w++) {
@@ -743,15 +721,13 @@ k_bitslice(BitsliceArgs a)
                 }
             }
             __syncwarp();
-            slot0 += nrows;
-            slot0 = slot0 >= NR ? slot0 - NR : slot0;
             mslot0 += nrows;
             mslot0 = mslot0 >= NRM ? mslot0 - NRM : mslot0;
             tslot = (tslot + nrows) % N;
         }
     }
 
-    if constexpr (TM) {
+    {
         tm_wait_st();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -760,14 +736,19 @@ k_bitslice(BitsliceArgs a)
     }
 }
 
-template <int HALF, int NW, int SEG, bool C2, bool TM>
-int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand, int max_cand)
+template <int HALF, int NW, int SEG, bool C2>
+int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
 {
-    using C = WS<HALF, NW, SEG, TM>;
+    using C = WS<HALF, NW, SEG>;
     // MULTI: more than one chunk of 32*NW shifts, i.e. (best, web) are merged across passes
-    const bool multi = !C2 && h.g.D > 32 * NW;
-    auto kern = C2 ? k_bitslice<HALF, NW, SEG, false, C2, TM>
-                   : (multi ? k_bitslice<HALF, NW, SEG, true, false, TM> : k_bitslice<HALF, NW, SEG, false, false, TM>);
+    // (one word per lane is only chosen for 32 shifts or fewer: no MULTI flavour of it is instantiated)
+    const bool multi = !C2 && NW == 2 && h.g.D > 32 * NW;
+    if (!C2 && !multi && h.g.D > 32 * NW) {
+        set_error("bit-sliced kernel: %d shifts need two shift words per lane", h.g.D);
+        return SM_ERR_ARG;
+    }
+    auto kern = C2 ? k_bitslice<HALF, NW, SEG, false, C2>
+                   : (multi ? k_bitslice<HALF, NW, SEG, NW == 2, false> : k_bitslice<HALF, NW, SEG, false, false>);
     // the resident warps per SM of this instantiation on the current device: asked once per context
     // (prepare_bitslice at sm_create, kept in HotArgs::blocks_per_sm), never cached in a static
     int warps_per_sm = h.blocks_per_sm;
@@ -794,30 +775,36 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *can
         rows = (rows + C::RB - 1) / C::RB * C::RB;
         return (h.g.BH + rows - 1) / rows;
     };
-    if (mode == MODE_CANDIDATES) {
-        // launch shapes worth timing for one pair per launch: from half a wave of resident warps
-        // to several waves (short runs pay more window-filling rows, long runs balance worse)
-        const double f[] = {0.5, 0.625, 0.75, 0.875, 1.0, 1.25, 1.5, 2.0, 2.5, 3.0, 4.0};
-        int n = 0;
-        for (double x : f) {
-            int rows, sg = shape((int)(x * num_sms * warps_per_sm / strips), rows);
-            bool seen = false;
-            for (int k = 0; k < n; k++) seen |= cand[k] == sg;
-            if (!seen && n < max_cand) cand[n++] = sg;
-        }
-        return n;
-    }
+    // CTA slots of the machine and CTAs per row run of one pair
+    const int slots = num_sms * warps_per_sm / C::WPC > 0 ? num_sms * warps_per_sm / C::WPC : 1;
+    const int ctas_per_run = (strips + C::WPC - 1) / C::WPC;
     int segs;
-    if (h.npairs == 1) {
-        // latency mode (one pair): the shape timed best at sm_create (force_segs), else one full
-        // wave of resident warps
-        segs = h.force_segs > 0 ? h.force_segs : num_sms * warps_per_sm / strips;
+    if (h.force_segs > 0) {
+        segs = h.force_segs;  // development hook (sm_set_option)
+    } else if (h.npairs == 1) {
+        // latency mode (one pair per launch).  All CTAs do the same work: a run of R rows costs R + 2*half
+        // window-filling rows + a fixed start-up, and the launch takes as many rounds of that as its CTAs need
+        // waves of the machine.  Pick the number of runs that minimises rounds x cost (short runs pay more
+        // filling rows, long runs leave slots empty); a cost model instead of timing candidates at sm_create.
+        const int start_rows = 4;
+        long best_cost = -1;
+        segs = 1;
+        for (int sg = 1; sg <= max_segs; sg++) {
+            int rows, got = shape(sg, rows);
+            if (got != sg) continue;
+            const long waves = ((long)ctas_per_run * got + slots - 1) / slots;
+            const long cost = waves * (rows + 2 * HALF + start_rows);
+            if (best_cost < 0 || cost < best_cost) best_cost = cost, segs = got;
+            if (waves > 4) break;
+        }
     } else {
-        // throughput mode (several pairs per launch): runs of about 32 windows, whatever the
-        // number of CTAs -- the launch may be several waves deep, the block scheduler keeps the
-        // slots full and the next launch (other stream) covers the tail
+        // throughput mode (several pairs per launch): runs of about 32 windows -- the launch may be several waves
+        // deep, the block scheduler keeps the slots full and the next launch (other stream) covers the tail --
+        // but never so few CTAs that one launch cannot fill the machine once
         const int want = throughput_run_windows() * C::N;
         segs = (h.g.BH + want - 1) / want;
+        const int fill = (slots + ctas_per_run * h.npairs - 1) / (ctas_per_run * h.npairs);
+        if (segs < fill) segs = fill;
     }
     segs = shape(segs, a.rows_per_seg);
     dim3 grid((strips + C::WPC - 1) / C::WPC, segs, h.npairs);
@@ -849,7 +836,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *can
 //          Measured on config 2 (us per pair, batched): 8 -> 18.2, 16 -> 18.0, 32 -> 25.2.
 struct Shape {
     int nw, seg;
-    bool c2, tm;
+    bool c2;
 };
 
 constexpr int C2_MAX_HALF = 6;
@@ -858,7 +845,6 @@ static Shape pick_shape(const HotArgs &h)
 {
     Shape sh;
     sh.seg = 16;
-    sh.tm = false;
     if (h.g.D > 32) {
         sh.nw = 2;
         sh.c2 = false;
@@ -870,34 +856,27 @@ static Shape pick_shape(const HotArgs &h)
     if (getenv("SMB_NO_C2") && atoi(getenv("SMB_NO_C2")) && sh.c2) sh.c2 = false, sh.nw = 1;
     if (getenv("SMB_NW") && !sh.c2) sh.nw = atoi(getenv("SMB_NW"));
     if (getenv("SMB_SEG")) sh.seg = atoi(getenv("SMB_SEG"));
-    if (getenv("SMB_TM")) sh.tm = atoi(getenv("SMB_TM")) != 0;
 #endif
     return sh;
 }
 
-static int dispatch(const HotArgs &h, int num_sms, cudaStream_t s, int mode, int *cand = nullptr, int max_cand = 0)
+static int dispatch(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
 {
     const Shape sh = pick_shape(h);
     const int half = h.g.half;
-#define SM_SHAPE_TM(HF, NW_, SEG_, C2_, TM_) \
-    if (half == HF && sh.nw == NW_ && sh.seg == SEG_ && sh.c2 == C2_ && sh.tm == TM_) \
-        return launch_one<HF, NW_, SEG_, C2_, TM_>(h, num_sms, s, mode, cand, max_cand);
+#define SM_SHAPE(HF, NW_, SEG_, C2_) \
+    if (half == HF && sh.nw == NW_ && sh.seg == SEG_ && sh.c2 == C2_) \
+        return launch_one<HF, NW_, SEG_, C2_>(h, num_sms, s, mode);
 #define SM_HALVES(M, ...) \
     M(0, __VA_ARGS__) M(1, __VA_ARGS__) M(2, __VA_ARGS__) M(3, __VA_ARGS__) M(4, __VA_ARGS__) M(5, __VA_ARGS__) \
     M(6, __VA_ARGS__) M(7, __VA_ARGS__) M(8, __VA_ARGS__) M(9, __VA_ARGS__) M(10, __VA_ARGS__) M(11, __VA_ARGS__) \
     M(12, __VA_ARGS__) M(13, __VA_ARGS__) M(14, __VA_ARGS__) M(15, __VA_ARGS__)
-    SM_HALVES(SM_SHAPE_TM, 1, 16, false, false)
-    SM_HALVES(SM_SHAPE_TM, 2, 16, false, false)
-    SM_HALVES(SM_SHAPE_TM, 1, 16, false, true)
-    SM_HALVES(SM_SHAPE_TM, 2, 16, false, true)
-#define SM_C2(TM_) \
-    SM_SHAPE_TM(0, 2, 16, true, TM_) SM_SHAPE_TM(1, 2, 16, true, TM_) SM_SHAPE_TM(2, 2, 16, true, TM_) \
-    SM_SHAPE_TM(3, 2, 16, true, TM_) SM_SHAPE_TM(4, 2, 16, true, TM_) SM_SHAPE_TM(5, 2, 16, true, TM_) \
-    SM_SHAPE_TM(6, 2, 16, true, TM_)
-    SM_C2(false) SM_C2(true)
-#undef SM_C2
+    SM_HALVES(SM_SHAPE, 1, 16, false)
+    SM_HALVES(SM_SHAPE, 2, 16, false)
+    SM_SHAPE(0, 2, 16, true) SM_SHAPE(1, 2, 16, true) SM_SHAPE(2, 2, 16, true) SM_SHAPE(3, 2, 16, true)
+    SM_SHAPE(4, 2, 16, true) SM_SHAPE(5, 2, 16, true) SM_SHAPE(6, 2, 16, true)
 #undef SM_HALVES
-#undef SM_SHAPE_TM
+#undef SM_SHAPE
     set_error("bit-sliced kernel: window half %d with %d word(s) per lane and %d-column walks is not instantiated",
               half, sh.nw, sh.seg);
     return SM_ERR_ARG;
@@ -917,25 +896,19 @@ int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s) { return disp
 // per launch, 18.3 us with 12 or more).
 int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 {
-    // enough pairs that one launch is a few waves of warps (about 8 resident per SM)
+    // enough pairs that one launch is about three waves of the warps the SMs hold (HotArgs::blocks_per_sm)
     const int strip_cols = pick_shape(h).c2 ? 64 : 32;
     const int N = 2 * h.g.half + 1, strips = (h.g.W + strip_cols - 1) / strip_cols;
     const int want = throughput_run_windows() * N;
     const int segs = (h.g.BH + want - 1) / want > 0 ? (h.g.BH + want - 1) / want : 1;
+    const int warps_per_sm = h.blocks_per_sm > 0 ? h.blocks_per_sm : 8;
     int p = 1;
-    while (p < max_pairs && strips * segs * p < 3 * num_sms * 8) p++;
+    while (p < max_pairs && strips * segs * p < 3 * num_sms * warps_per_sm) p++;
     return p;
 }
 
 // Loads the kernel this geometry will use and sets its shared-memory attribute, so that the first
 // sm_match_wta call pays none of that; returns its resident warps per SM (for HotArgs::blocks_per_sm).
 int prepare_bitslice(const HotArgs &h, int num_sms) { return dispatch(h, num_sms, nullptr, MODE_PREPARE); }
-
-// Launch shapes (number of row runs per strip) worth timing for a single-pair launch of this
-// geometry; sm_create times them and keeps the fastest (HotArgs::force_segs).
-int bitslice_seg_candidates(const HotArgs &h, int num_sms, int *cand, int max_cand)
-{
-    return dispatch(h, num_sms, nullptr, MODE_CANDIDATES, cand, max_cand);
-}
 
 }  // namespace smb

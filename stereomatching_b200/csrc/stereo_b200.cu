@@ -47,7 +47,7 @@ struct sm_ctx {
     cudaEvent_t *prof_ev = nullptr;
     int prof_cap = 0, prof_n = 0;
     int last_launches = 0;
-    int tuned_segs = 0;  // single-pair launch shape of the bit-sliced kernel, timed at create (0: default)
+    int tuned_segs = 0;  // SM_OPT_ROW_RUNS: row runs per strip of a one-pair launch (0: the kernel's cost model)
     int occ = 0;         // resident warps per SM of the bit-sliced kernel of this geometry (prepare_bitslice)
 
     // frame-sized device arrays (a band context touches only the rows it needs)
@@ -58,7 +58,8 @@ struct sm_ctx {
     bool have_edges = false;
     uint32_t *edge_lut = nullptr;  // detector decisions for all (L, R) sum pairs at lut_threshold
     double lut_threshold = -1.0;
-    bool edges_fp64_only = false;  // SM_EDGES_FP64=1: always take the FP64 kernel (cross-check)
+    bool edges_fp64_only = false;  // SM_OPT_EDGES_FP64: always take the FP64 kernel (cross-check)
+    int pipe_group_opt = 0;        // SM_OPT_PIPE_GROUP: pairs per sm_run_batch stage (0: by frame size)
     int32_t *best = nullptr, *web = nullptr;
     bool have_web = false;
     int32_t *web2 = nullptr, *tmp = nullptr;  // step 3 ping-pong
@@ -75,7 +76,9 @@ struct sm_ctx {
     static constexpr int NPB = 3;
     cudaStream_t pack_stream = nullptr, main2_stream = nullptr;  // main kernels alternate stream / main2_stream
     cudaEvent_t ev_join = nullptr;
-    int batch_group = 1;  // pairs per launch in sm_match_wta_dev_batch
+    int batch_group = 1;      // pairs per launch in sm_match_wta_dev_batch (1 for the literal kernel)
+    int batch_group_cap = 0;  // ... of the bit-sliced kernel; the plane sets are sized for it
+    bool batch_ready = false;
     uint32_t *pLA[NPB] = {nullptr, nullptr, nullptr}, *pLB[NPB] = {nullptr, nullptr, nullptr},
              *pRB[NPB] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_packed[NPB] = {nullptr, nullptr, nullptr}, ev_used[NPB] = {nullptr, nullptr, nullptr};
@@ -89,6 +92,7 @@ struct sm_ctx {
     static constexpr int NPIPE = 3;
     struct Pipe {
         int group = 0;  // pairs per stage
+        bool ready = false;
         cudaStream_t up = nullptr, down = nullptr;
         uint8_t *img[NPIPE] = {nullptr, nullptr, nullptr};    // [2*group][npix]: first images, then second images
         uint8_t *edg[NPIPE] = {nullptr, nullptr, nullptr};    // same layout
@@ -255,53 +259,6 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
     return SM_OK;
 }
 
-// Time the single-pair launch shapes the kernel proposes for this geometry and keep the
-// fastest: between half a wave and several waves of warps the best run length depends on the
-// frame height, the window and the occupancy in ways a formula misses (measured: 4K / 256
-// shifts / window 11 is 16 % faster two waves deep, 1080p / window 21 is fastest at exactly
-// one).  What is timed is what callers run: pack + main kernel (programmatic dependent launch)
-// several times back to back, on whatever bytes the edge buffers hold (the kernels are
-// branch-free in the data).  Part of the untimed set-up.
-int tune_launch_shape(sm_ctx *c)
-{
-    HotArgs a = hot_args(c, c->best, c->web);
-    int cand[16];
-    const int n = bitslice_seg_candidates(a, c->num_sms, cand, 16);
-    if (n <= 1) return SM_OK;
-    SM_CUDA(cudaMemsetAsync(c->edges[0], 1, c->npix(), c->stream));
-    SM_CUDA(cudaMemsetAsync(c->edges[1], 0, c->npix(), c->stream));
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    SM_CUDA(cudaEventCreate(&e0));
-    SM_CUDA(cudaEventCreate(&e1));
-    float best_ms = 1e30f;
-    int best_segs = 0, rc = SM_OK;
-    for (int k = 0; k < n && rc == SM_OK; k++) {
-        c->tuned_segs = cand[k];
-        float tmin = 1e30f, warm_ms = 0.f;
-        for (int rep = 0; rep < 4 && rc == SM_OK; rep++) {  // rep 0 warms up
-            const int calls = rep == 0 ? 1 : (warm_ms > 0.15f ? 2 : 4);  // long kernels: fewer repeats
-            cudaEventRecord(e0, c->stream);
-            for (int j = 0; j < calls && rc == SM_OK; j++) rc = run_hot(c, c->edges[0], c->edges[1], c->best, c->web);
-            cudaEventRecord(e1, c->stream);
-            if (cudaEventSynchronize(e1) != cudaSuccess) rc = SM_ERR_CUDA;
-            float ms = 0;
-            cudaEventElapsedTime(&ms, e0, e1);
-            if (rep == 0) warm_ms = ms;
-            if (rep > 0 && ms / calls < tmin) tmin = ms / calls;
-        }
-        if (tmin < best_ms) {
-            best_ms = tmin;
-            best_segs = cand[k];
-        }
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    c->tuned_segs = rc == SM_OK ? best_segs : 0;
-    c->timed = false;
-    c->last_launches = 0;
-    return rc;
-}
-
 void profile_free(sm_ctx *c)
 {
     for (int k = 0; k < 3 * c->prof_cap; k++)
@@ -391,7 +348,6 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
     c->g.ER = c->g.BH + 2 * c->half;
     c->g.D = num_shifts;
     c->g.WPR = packed_words_per_row(width, c->half, num_shifts);
-    c->edges_fp64_only = getenv("SM_EDGES_FP64") && atoi(getenv("SM_EDGES_FP64")) != 0;
 
     int rc = SM_OK;
     auto fail = [&](int code) {
@@ -428,7 +384,6 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
         HotArgs a = hot_args(c, c->best, c->web);
         if ((rc = prepare_bitslice(a, c->num_sms)) < 0) return fail(rc);
         c->occ = rc;
-        if (!(getenv("SMB_NO_TUNE") && atoi(getenv("SMB_NO_TUNE"))) && (rc = tune_launch_shape(c)) < 0) return fail(rc);
     }
     *out = c;
     return SM_OK;
@@ -507,6 +462,24 @@ extern "C" int sm_set_kernel(sm_ctx *c, int kernel)
     SM_REQUIRE(kernel >= SM_KERNEL_AUTO && kernel <= SM_KERNEL_BITSLICE, "sm_set_kernel: unknown kernel");
     c->kernel = kernel;
     return SM_OK;
+}
+
+extern "C" int sm_set_option(sm_ctx *c, int option, int value)
+{
+    SM_ENTER(c);
+    switch (option) {
+    case SM_OPT_EDGES_FP64: c->edges_fp64_only = value != 0; return SM_OK;
+    case SM_OPT_PIPE_GROUP:
+        SM_REQUIRE(value >= 0 && value <= 1024, "sm_set_option: pairs per stage must be in [0, 1024]");
+        SM_REQUIRE(!c->pipe.ready, "sm_set_option: the batch pipeline of this context is already set up");
+        c->pipe_group_opt = value;
+        return SM_OK;
+    case SM_OPT_ROW_RUNS:
+        SM_REQUIRE(value >= 0, "sm_set_option: row runs must be >= 0");
+        c->tuned_segs = value;
+        return SM_OK;
+    default: set_error("sm_set_option: unknown option %d", option); return SM_ERR_ARG;
+    }
 }
 
 extern "C" int sm_synchronize(sm_ctx *c)
@@ -645,32 +618,41 @@ extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_f
     SM_REQUIRE(edge_stride >= c->npix() && out_stride >= c->npix(), "sm_match_wta_dev_batch: stride below frame size");
     constexpr int NPB = sm_ctx::NPB;
     const size_t pw = (size_t)c->g.ER * c->g.WPR;
-    if (!c->pack_stream) {
-        // pairs per launch: enough that every warp's run of rows is long against its warm-up rows
-        int kk = c->kernel;
-        if (kk == SM_KERNEL_AUTO) kk = bitslice_supports(c->half, c->D) ? SM_KERNEL_BITSLICE : SM_KERNEL_DIRECT;
-        c->batch_group = 1;
-        if (kk == SM_KERNEL_BITSLICE) {
-            HotArgs a = hot_args(c, d_best, d_web);
-            int pmax = 16;
+    int kk = c->kernel;
+    if (kk == SM_KERNEL_AUTO) kk = bitslice_supports(c->half, c->D) ? SM_KERNEL_BITSLICE : SM_KERNEL_DIRECT;
+    if (!c->batch_ready) {
+        // Set-up of the batch path.  Every object is created only if it does not exist yet and the ready flag is
+        // set last, so that a call that failed half way (out of memory on the plane sets, say) is simply resumed
+        // by the next one instead of launching with missing buffers.
+        // Pairs per launch: enough that every warp's run of rows is long against its warm-up rows
+        if (c->batch_group_cap == 0) {
+            c->batch_group_cap = 1;
+            if (bitslice_supports(c->half, c->D)) {
+                HotArgs a = hot_args(c, d_best, d_web);
+                int pmax = 16;
 #ifdef SMB_DEV
-            if (getenv("SMB_PMAX")) pmax = atoi(getenv("SMB_PMAX"));  // experiment hook, development build only
+                if (getenv("SMB_PMAX")) pmax = atoi(getenv("SMB_PMAX"));  // experiment hook, development build only
 #endif
-            c->batch_group = bitslice_pairs_per_launch(a, c->num_sms, pmax);
+                c->batch_group_cap = bitslice_pairs_per_launch(a, c->num_sms, pmax);
+            }
         }
-        SM_CUDA(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
-        SM_CUDA(cudaStreamCreateWithFlags(&c->main2_stream, cudaStreamNonBlocking));
-        SM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        SM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        if (!c->pack_stream) SM_CUDA(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
+        if (!c->main2_stream) SM_CUDA(cudaStreamCreateWithFlags(&c->main2_stream, cudaStreamNonBlocking));
+        if (!c->ev_fork) SM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        if (!c->ev_join) SM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         for (int k = 0; k < NPB; k++) {
             int rc;
-            if ((rc = dev_alloc(&c->pLA[k], pw * c->batch_group)) || (rc = dev_alloc(&c->pLB[k], pw * c->batch_group)) ||
-                (rc = dev_alloc(&c->pRB[k], pw * c->batch_group)))
+            if ((rc = dev_alloc(&c->pLA[k], pw * c->batch_group_cap)) || (rc = dev_alloc(&c->pLB[k], pw * c->batch_group_cap)) ||
+                (rc = dev_alloc(&c->pRB[k], pw * c->batch_group_cap)))
                 return rc;
-            SM_CUDA(cudaEventCreateWithFlags(&c->ev_packed[k], cudaEventDisableTiming));
-            SM_CUDA(cudaEventCreateWithFlags(&c->ev_used[k], cudaEventDisableTiming));
+            if (!c->ev_packed[k]) SM_CUDA(cudaEventCreateWithFlags(&c->ev_packed[k], cudaEventDisableTiming));
+            if (!c->ev_used[k]) SM_CUDA(cudaEventCreateWithFlags(&c->ev_used[k], cudaEventDisableTiming));
         }
+        c->batch_ready = true;
     }
+    // the kernel may have been switched since the last call (sm_set_kernel): the literal kernel takes one pair
+    // per launch, the bit-sliced one a group
+    c->batch_group = kk == SM_KERNEL_BITSLICE ? c->batch_group_cap : 1;
     const int G = c->batch_group;
     // everything queued on the context's stream so far (the producers of the edge maps) comes first
     SM_CUDA(cudaEventRecord(c->ev0, c->stream));
@@ -957,22 +939,24 @@ extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const 
     sm_ctx::Pipe &P = c->pipe;
     const size_t n = c->npix();
     int rc;
-    if (!P.up) {
+    if (!P.ready) {  // resumable set-up, ready flag last (see sm_match_wta_dev_batch)
         // pairs per stage: enough for the batched hot path to run in throughput mode, bounded
         // so that the three buffer sets stay small against HBM (16 B per pixel and pair)
-        P.group = n <= ((size_t)1 << 22) ? 16 : (n <= ((size_t)1 << 24) ? 8 : 2);
-        if (getenv("SMB_PIPE_GROUP")) P.group = atoi(getenv("SMB_PIPE_GROUP"));  // tests: many stages from few pairs
-        if (P.group < 1) P.group = 1;
-        SM_CUDA(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
-        SM_CUDA(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
+        if (P.group == 0) {
+            P.group = n <= ((size_t)1 << 22) ? 16 : (n <= ((size_t)1 << 24) ? 8 : 2);
+            if (c->pipe_group_opt > 0) P.group = c->pipe_group_opt;
+        }
+        if (!P.up) SM_CUDA(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
+        if (!P.down) SM_CUDA(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
         for (int k = 0; k < NP; k++) {
             if ((rc = dev_alloc(&P.img[k], 2 * P.group * n)) || (rc = dev_alloc(&P.edg[k], 2 * P.group * n)) ||
                 (rc = dev_alloc(&P.web[k], P.group * n)) || (rc = dev_alloc(&P.best[k], P.group * n)))
                 return rc;
-            SM_CUDA(cudaEventCreateWithFlags(&P.ev_up[k], cudaEventDisableTiming));
-            SM_CUDA(cudaEventCreateWithFlags(&P.ev_comp[k], cudaEventDisableTiming));
-            SM_CUDA(cudaEventCreateWithFlags(&P.ev_down[k], cudaEventDisableTiming));
+            if (!P.ev_up[k]) SM_CUDA(cudaEventCreateWithFlags(&P.ev_up[k], cudaEventDisableTiming));
+            if (!P.ev_comp[k]) SM_CUDA(cudaEventCreateWithFlags(&P.ev_comp[k], cudaEventDisableTiming));
+            if (!P.ev_down[k]) SM_CUDA(cudaEventCreateWithFlags(&P.ev_down[k], cudaEventDisableTiming));
         }
+        P.ready = true;
     }
     if (web_u8)
         for (int k = 0; k < NP; k++)

@@ -107,10 +107,11 @@ def main():
     ap.add_argument("--md", default=None)
     a = ap.parse_args()
     import oracle
+    import benchlib
     import stereomatching_b200 as smb
     from util import FIXTURES, load_pair
     orc = oracle.Oracle()
-    peak = max(smb.measure_int_peak(0, m) for m in range(4))
+    peak = max(benchlib.measure_int_peak(0, m) for m in range(4))
     rows = []
     what = a.what.split(",")
 

@@ -168,17 +168,18 @@ def test_windows_beyond_the_bitsliced_kernel(orc):
             _run_edges(c, z, z)
 
 
-def test_tuned_and_default_launch_shapes_agree(orc, monkeypatch):
+def test_launch_shapes_agree(orc):
     # the launch shape timed at sm_create changes how rows are split into runs, never the result
     w, h, D, sw = 640, 360, 64, 9
     left, right, _ = orc.synth_pair(4321, w, h, D)
     for variant in (smb.WRAP, smb.GHOST):
         e1, e2 = orc.edges(left, THRESHOLD, variant), orc.edges(right, THRESHOLD, variant)
         res = []
-        for no_tune in ("0", "1"):
-            monkeypatch.setenv("SMB_NO_TUNE", no_tune)
+        for runs in (0, 1, 5):  # the cost model's launch shape, one run per strip, five
             with _ctx(w, h, D, sw, variant) as c:
+                c.set_option(smb.OPT_ROW_RUNS, runs)
                 res.append(_run_edges(c, e1, e2))
+        assert np.array_equal(res[0][0], res[2][0]) and np.array_equal(res[0][1], res[2][1])
         assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
         bo, wo = orc.match_wta(e1, e2, D, sw, variant)
         assert np.array_equal(res[0][0], bo) and np.array_equal(res[0][1], wo)
@@ -320,15 +321,34 @@ def test_run_batch_equals_single_pairs(orc):
             assert np.array_equal(web8[k], wo.astype(np.uint8))
 
 
-def test_run_batch_pipeline_many_stages(orc, monkeypatch):
+def test_batch_kernel_switch_on_one_context(orc):
+    """sm_set_kernel between two batch calls with DIFFERENT inputs: the literal kernel must compute every pair
+    of the second call (it runs one pair per launch whatever group size the bit-sliced kernel used before)."""
+    n, w, h, D, sw = 9, 160, 72, 40, 7
+    a = [orc.synth_pair(300 + 2 * k, w, h, D) for k in range(n)]
+    b = [orc.synth_pair(900 + 2 * k, w, h, D) for k in range(n)]
+    with _ctx(w, h, D, sw, smb.WRAP) as c:
+        c.run_batch(np.stack([p[0] for p in a]), np.stack([p[1] for p in a]), THRESHOLD)
+        c.set_kernel(smb.KERNEL_DIRECT)
+        web, best = c.run_batch(np.stack([p[0] for p in b]), np.stack([p[1] for p in b]), THRESHOLD, want_best=True)
+        c.set_kernel(smb.KERNEL_BITSLICE)
+        web2 = c.run_batch(np.stack([p[0] for p in b]), np.stack([p[1] for p in b]), THRESHOLD)
+    for k in range(n):
+        e1, e2 = orc.edges(b[k][0], THRESHOLD, smb.WRAP), orc.edges(b[k][1], THRESHOLD, smb.WRAP)
+        bo, wo = orc.match_wta(e1, e2, D, sw, smb.WRAP)
+        assert np.array_equal(web[k], wo) and np.array_equal(best[k], bo), k
+        assert np.array_equal(web2[k], wo), k
+
+
+def test_run_batch_pipeline_many_stages(orc):
     # groups of 2 pairs: 11 pairs = 6 stages over the 3 buffer sets, ragged last stage; two calls on one context
-    monkeypatch.setenv("SMB_PIPE_GROUP", "2")
     n, w, h, D, sw = 11, 200, 96, 40, 7
     pairs = [orc.synth_pair(77 + 2 * k, w, h, D) for k in range(n)]
     first = np.stack([p[0] for p in pairs])
     second = np.stack([p[1] for p in pairs])
     for variant in (smb.WRAP, smb.GHOST):
         with _ctx(w, h, D, sw, variant) as c:
+            c.set_option(smb.OPT_PIPE_GROUP, 2)
             web, best = c.run_batch(first, second, THRESHOLD, want_best=True)
             web8 = c.run_batch(first[::-1].copy(), second[::-1].copy(), THRESHOLD, web_u8=True)
         for k in range(n):

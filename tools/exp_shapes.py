@@ -26,10 +26,13 @@ POINTS = {
     "w17d32": (1920, 1080, 32, 17),
     "c3": (3840, 2160, 256, 11),
     "w3": (1920, 1080, 64, 3),
+    "w11": (1920, 1080, 64, 11),
+    "w13": (1920, 1080, 64, 13),
+    "w5": (1920, 1080, 64, 5),
     "w1": (1920, 1080, 30, 1),
     "c2d32": (1920, 1080, 32, 9),
 }
-SHAPES = [{}, {"SMB_TM": "1"}]
+SHAPES = [{}]
 EXTRA = [{"SMB_TR": "16"}, {"SMB_TR": "64"}]
 
 
@@ -110,6 +113,8 @@ if __name__ == "__main__":
     if "--default-only" in sys.argv:  # one shape, small batch: the command line for ncu
         os.environ["SMB_NO_TUNE"] = "1"
         SHAPES[:] = [{k: v for k, v in (kv.split("=") for kv in os.environ.get("EXP_SHAPE", "").split(",") if kv)}]
+        EXTRA[:] = []
+    if "--no-extra" in sys.argv:
         EXTRA[:] = []
     for p in (args or ["c4", "ref30", "w15", "w17", "w21d64", "c2", "c3", "w3", "w1", "c2d32"]):
         run_point(p, batch=16 if "--default-only" in sys.argv else (12 if p == "c3" else 48))
