@@ -186,6 +186,12 @@ def run_reference_arm(a, rank):
     rows, half = 24, SW // 2
     ctx = mp.get_context("fork")
     kind = "reference"
+    try:  # the library the workers run is loaded here as well, so that the process record shows what ran
+        import oracle
+        if oracle.ref_available(0, D):
+            oracle.RefLib(0, D)
+    except OSError:
+        pass
     with ctx.Pool(cores) as pool:
         def step(s):
             nonlocal kind
@@ -214,39 +220,223 @@ def run_reference_arm(a, rank):
 # ------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------
-def bind_to_gpu_numa_node(local_rank):
-    """Run this rank on the CPUs next to its GPU (NVML's ideal affinity) so that the pinned staging buffers of
-    the end-to-end leg are first-touched on the GPU's own NUMA node.  Best effort; returns what was done."""
+def bind_rank_to_cpus(local_rank, local_world):
+    """Give every rank of the node its own, disjoint slice of the CPUs this job may use, so that eight ranks do not
+    all run (and first-touch their pinned staging buffers) on the same cores.  Where NVML knows the CPUs next to the
+    GPU the slice is taken from those.  Best effort; returns what was done."""
     try:
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
-        pynvml.nvmlDeviceSetCpuAffinity(h)
-        cpus = sorted(os.sched_getaffinity(0))
-        return "cpus %d-%d (%d)" % (cpus[0], cpus[-1], len(cpus))
+        allowed = sorted(os.sched_getaffinity(0))
+        near = allowed
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(allowed) + 64) // 64)
+            ideal = [c for c in allowed if (words[c // 64] >> (c % 64)) & 1]
+            if len(ideal) >= max(2, len(allowed) // max(local_world, 1)):
+                near = ideal
+        except Exception:  # noqa: BLE001
+            pass
+        n = max(1, len(near) // max(local_world, 1))
+        mine = near[(local_rank * n) % len(near):][:n] or near
+        os.sched_setaffinity(0, mine)
+        return "cpus %s (%d of %d allowed)" % (",".join(map(str, mine[:4])) + ("..." if len(mine) > 4 else ""),
+                                               len(mine), len(allowed))
     except Exception as e:  # noqa: BLE001
         return "not bound: %s" % type(e).__name__
-def run_b200_arm(a, rank, world, local_rank):
-    import torch
-    import torch.distributed as dist
 
+
+class Env:
+    """Rank bookkeeping: barrier, max over ranks (gloo control plane; the data path has no collective)."""
+
+    def __init__(self, rank, world, local_rank):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        if world > 1:
+            # control plane only (barrier + max of the per-rank time): the data path has no exchange step,
+            # so no NCCL communicator is ever needed (SURVEY 8e); gloo keeps stdout to the one JSON line
+            dist.init_process_group("gloo")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def rmax(self, x):
+        if self.world > 1:
+            t = self.torch.tensor([x], dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def all_true(self, ok):
+        return self.rmax(0.0 if ok else 1.0) == 0.0
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def _crc(a):
+    import zlib
+    return "%08x" % (zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xFFFFFFFF)
+
+
+def _golden():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+
+
+def time_batches(env, ctx, stream, run, steps):
+    """steps calls of run() on the context's stream, device-timed, max over ranks -> ms per step."""
+    torch = env.torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.barrier()
+    ev0.record(stream)
+    for _ in range(steps):
+        run()
+    ev1.record(stream)
+    env.barrier()
+    return env.rmax(ev0.elapsed_time(ev1)) / steps
+
+
+def leg_config4_pairs(env, smb, variant_name, npairs=64):
+    """BASELINE configs[3]: whole 1280x720 pairs, 128 shifts, window 21 (the reference's default window), sharded
+    over the ranks as whole pairs; `npairs` per GPU and step, resident and end to end (u8 web), every distinct
+    pair's web checked against the reference's golden CRC."""
+    torch = env.torch
+    w, h, d, sw = 1280, 720, 128, 21
+    g = _golden()
+    variant = smb.GHOST if variant_name == "ghost" else smb.WRAP
+    keys = ["synth/c4/%d/%s" % (k, variant_name) for k in range(4)]
+    pairs = [synth_pair(g[k]["seed"], w, h, d) for k in keys]
+    first = np.stack([pairs[k % 4][0] for k in range(npairs)])
+    second = np.stack([pairs[k % 4][1] for k in range(npairs)])
+    out = {"workload": "%d synthetic 1280x720 pairs per GPU and step, 128 shifts, window 21x21 (BASELINE configs[3]; "
+                       "4 distinct pairs, seeds 1234+2k)" % npairs}
+    with smb.StereoContext(w, h, d, sw, variant, device=env.local_rank) as c:
+        stream = torch.cuda.Stream(device=env.dev)
+        c.set_stream(stream.cuda_stream)
+        # edge maps resident: detect them once per distinct pair
+        e1 = torch.empty((npairs, h, w), dtype=torch.uint8, device=env.dev)
+        e2 = torch.empty_like(e1)
+        for k in range(4):
+            c.upload_u8(pairs[k][0], pairs[k][1])
+            c.edges(THRESHOLD)
+            e1[k] = torch.from_numpy(c.download(smb.EDGES1)).to(env.dev)
+            e2[k] = torch.from_numpy(c.download(smb.EDGES2)).to(env.dev)
+        for k in range(4, npairs):
+            e1[k], e2[k] = e1[k % 4], e2[k % 4]
+        best = torch.empty((npairs, h, w), dtype=torch.int32, device=env.dev)
+        web = torch.empty_like(best)
+        run = lambda: c.match_wta_dev_batch(npairs, e1.data_ptr(), e2.data_ptr(), h * w, best.data_ptr(),  # noqa: E731
+                                            web.data_ptr(), h * w)
+        for _ in range(3):
+            run()
+        ms = time_batches(env, c, stream, run, 5)
+        ok = all(_crc(web[k].cpu().numpy()) == g[keys[k % 4]]["web"] and
+                 _crc(best[k].cpu().numpy()) == g[keys[k % 4]]["best"] for k in (0, 1, 2, 3, npairs - 1))
+        out["resident"] = {"value": env.world * npairs * w * h * d / (ms * 1e-3) / 1e6, "unit": "MDE/s",
+                           "us_per_pair": ms * 1e3 / npairs, "pairs_per_s": env.world * npairs / (ms * 1e-3)}
+        # end to end: pinned host u8 images -> H2D -> edges -> hot path -> D2H u8 web
+        hin1, hin2 = smb.PinnedBuffer(first.shape, np.uint8), smb.PinnedBuffer(first.shape, np.uint8)
+        hweb = smb.PinnedBuffer(first.shape, np.uint8)
+        hin1.array[:], hin2.array[:] = first, second
+        c.run_batch(hin1.array, hin2.array, THRESHOLD, web_u8=True, web_out=hweb.array)
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            c.run_batch(hin1.array, hin2.array, THRESHOLD, web_u8=True, web_out=hweb.array)
+        env.barrier()
+        te = env.rmax(time.perf_counter() - t0) / 3
+        ok = ok and all(_crc(hweb.array[k].astype(np.int32)) == g[keys[k % 4]]["web"] for k in range(npairs))
+        out["e2e"] = {"value": env.world * npairs * w * h * d / te / 1e6, "unit": "MDE/s",
+                      "pairs_per_s": env.world * npairs / te, "api": "sm_run_batch(web_u8=1)",
+                      "h2d_bytes_per_step": 2 * npairs * w * h, "d2h_bytes_per_step": npairs * w * h}
+        hin1.free(), hin2.free(), hweb.free()
+    out["parity"] = {"equal_reference_golden": env.all_true(ok),
+                     "checked": "resident web+best of pairs 0-3 and the last; every e2e web (CRC32 vs tests/golden)"}
+    return out
+
+
+def leg_config3_bands(env, smb, variant_name):
+    """BASELINE configs[2]: ONE synthetic 3840x2160 pair, 256 shifts, window 11, as row bands with replicated
+    halo rows, one band per rank (strong scaling; the whole frame on one GPU when N = 1).  No exchange step:
+    every rank uploads its rows + half+1 halo rows per side and writes only its own rows."""
+    torch = env.torch
+    w, h, d, sw = 3840, 2160, 256, 11
+    g = _golden()["synth/c3/" + variant_name]
+    variant = smb.GHOST if variant_name == "ghost" else smb.WRAP
+    left, right, _ = synth_pair(g["seed"], w, h, d)
+    r0, r1 = smb.band_rows(h, env.world, env.rank)
+    pin_l, pin_r = smb.PinnedBuffer((h, w), np.uint8), smb.PinnedBuffer((h, w), np.uint8)
+    pin_web = smb.PinnedBuffer((h, w), np.int32)
+    pin_l.array[:], pin_r.array[:] = left, right
+    out = {"workload": "one synthetic 3840x2160 pair, 256 shifts, window 11x11, %d row band(s) with replicated halo "
+                       "rows (BASELINE configs[2])" % env.world, "rows_per_band": r1 - r0}
+    with smb.StereoContext(w, h, d, sw, variant, device=env.local_rank, rows=(r0, r1)) as c:
+        stream = torch.cuda.Stream(device=env.dev)
+        c.set_stream(stream.cuda_stream)
+        c.upload_u8(pin_l.array, pin_r.array)
+        c.edges(THRESHOLD)
+        # resident: the band's edge maps are on the device; a step = pack + match/box/WTA of the band
+        e1 = torch.from_numpy(c.download(smb.EDGES1)).to(env.dev)
+        e2 = torch.from_numpy(c.download(smb.EDGES2)).to(env.dev)
+        best = torch.empty((h, w), dtype=torch.int32, device=env.dev)
+        web = torch.empty_like(best)
+        run = lambda: c.match_wta_dev(e1.data_ptr(), e2.data_ptr(), best.data_ptr(), web.data_ptr())  # noqa: E731
+        for _ in range(3):
+            run()
+        ms = time_batches(env, c, stream, run, 10)
+        out["resident"] = {"value": w * h * d / (ms * 1e-3) / 1e6, "unit": "MDE/s", "ms_per_frame": ms,
+                           "scaling": "strong"}
+
+        def e2e_step():
+            c.upload_u8(pin_l.array, pin_r.array), c.edges(THRESHOLD), c.match_wta()
+            c.download(smb.WEB, out=pin_web.array)
+
+        e2e_step()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            e2e_step()
+        env.barrier()
+        te = env.rmax(time.perf_counter() - t0) / 5
+        out["e2e"] = {"value": w * h * d / te / 1e6, "unit": "MDE/s", "ms_per_frame": te * 1e3,
+                      "api": "sm_upload_u8 (band + halo rows) -> sm_edges -> sm_match_wta -> sm_download(SM_WEB) (band rows)"}
+        # parity: this rank's rows against the reference's golden CRCs of the 16 row bands of the whole frame
+        nb = len(g["web_bands16"])
+        mine = [b for b in range(nb) if r0 <= h * b // nb and h * (b + 1) // nb <= r1]
+        ok = len(mine) > 0 and all(_crc(pin_web.array[h * b // nb:h * (b + 1) // nb]) == g["web_bands16"][b] for b in mine)
+        ok = ok and all(_crc(web[h * b // nb:h * (b + 1) // nb].cpu().numpy()) == g["web_bands16"][b] for b in mine)
+    out["parity"] = {"bands_equal_reference_golden": env.all_true(ok),
+                     "checked": "each rank's rows of web (resident and e2e) vs the per-band CRC32s of the reference's "
+                                "whole-frame output (tests/golden synth/c3)"}
+    pin_l.free(), pin_r.free(), pin_web.free()
+    return out
+
+
+def run_b200_arm(a, rank, world, local_rank):
     import benchlib
     import stereomatching_b200 as smb
 
+    env = Env(rank, world, local_rank)
+    torch = env.torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(local_rank)
-    if world > 1:
-        # control plane only (barrier + max of the per-rank time): the data path has no exchange step,
-        # so no NCCL communicator is ever needed (SURVEY 8e); gloo keeps stdout to the one JSON line
-        dist.init_process_group("gloo")
+    dev = env.dev
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    binding = bind_rank_to_cpus(local_rank, local_world)
     variant = smb.GHOST if a.variant == "ghost" else smb.WRAP
     B, distinct = a.pairs, min(a.pairs, a.distinct)
+    gold = _golden()
 
     # ---- inputs: `distinct` synthetic pairs, edges computed on the device, replicated into B buffers
-    pairs = [synth_pair(1234 + 2 * (rank * distinct + k), W, H, D) for k in range(distinct)]
+    seeds = [1234 + 2 * (rank * distinct + k) for k in range(distinct)]
+    pairs = [synth_pair(s, W, H, D) for s in seeds]
     ctx = smb.StereoContext(W, H, D, SW, variant, device=local_rank, kernel=a.kernel)
     e1 = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
     e2 = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
@@ -270,41 +460,65 @@ def run_b200_arm(a, rank, world, local_rank):
         if a.no_overlap:
             for k in range(B):
                 ctx.match_wta_dev(p1 + k * n8, p2 + k * n8, pb + k * n32, pw + k * n32)
-        else:  # one call per batch: the pack of pair k+1 runs beside the main kernel of pair k
+        else:  # one call per batch: the pack of group k+1 runs beside the main kernel of group k
             ctx.match_wta_dev_batch(B, p1, p2, n8, pb, pw, n8)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(max(a.warmup, 3)):
         step()
-    barrier()
-    parity = None
-    if rank == 0 and a.variant in ("wrap", "ghost"):
-        import zlib
-        g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["synth/c2/" + a.variant]
-        crc = "%08x" % (zlib.crc32(web[0].cpu().numpy().tobytes()) & 0xFFFFFFFF)
-        parity = {"pair0_web_crc32": crc, "golden": g["web"], "equal": crc == g["web"]}
-        if crc != g["web"]:
-            raise SystemExit("bench.py: web of pair 0 differs from the reference's golden CRC: %r" % parity)
+    env.barrier()
 
+    # ---- parity on the timed path: EVERY distinct pair of this rank against the reference's golden CRC
+    def golden_of(k):
+        key = "synth/c2s/%d/wrap" % seeds[k] if a.variant == "wrap" else ("synth/c2/ghost" if seeds[k] == 1234 else None)
+        return gold.get(key) if key else None
+
+    def check_webs(get_web, n, what):
+        bad, checked = [], 0
+        for k in range(n):
+            gk = golden_of(k % distinct)
+            if gk is None:
+                continue
+            checked += 1
+            if _crc(get_web(k)) != gk["web"]:
+                bad.append(k)
+        if bad:
+            raise SystemExit("bench.py: %s: web of pairs %r differs from the reference's golden CRC" % (what, bad[:8]))
+        return checked
+
+    n_checked = check_webs(lambda k: web[k].cpu().numpy(), min(B, 2 * distinct), "resident")
+    parity = {"resident_webs_checked": n_checked, "equal_reference_golden": True,
+              "golden": "tests/golden/golden.json synth/c2s/<seed>/wrap: CRC32 of web produced by the unmodified stereo.c"}
+
+    # ---- the timed region: K steps, device-timed on the launching stream, max over ranks
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ctx.profile_begin(a.steps * B)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    env.barrier()
     tw0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(a.steps):
         step()
     ev1.record(stream)
-    barrier()
+    env.barrier()
     tw1 = time.perf_counter()
-    ms = ev0.elapsed_time(ev1)
-    n_calls, _, overl_ms = ctx.profile_read()
+    ms = env.rmax(ev0.elapsed_time(ev1))
     launches = a.steps * ctx.last_launches()  # per batch call: one pack + one main launch per group of pairs
-    # the dominant kernel timed ALONE (one pair per call, nothing overlapped): the roofline figure
+    clocks = sampler.stop(tw0, tw1) if sampler else None
+    mde_step = B * W * H * D
+    value = world * mde_step * a.steps / (ms * 1e-3) / 1e6
+    us_pair_tp = ms * 1e3 / a.steps / B
+
+    # ---- sustained: the same step back to back for >= 2 s, its own clocks sample
+    sampler2 = ClockSampler(local_rank) if rank == 0 else None
+    n_sus = max(1, int(2.2 / max(ms * 1e-3 / a.steps, 1e-4)))
+    env.barrier()
+    ts0 = time.perf_counter()
+    ms_sus = time_batches(env, ctx, stream, step, n_sus)
+    ts1 = time.perf_counter()
+    clocks_sus = sampler2.stop(ts0, ts1) if sampler2 else None
+    sustained = {"value": world * mde_step / (ms_sus * 1e-3) / 1e6, "unit": "MDE/s", "steps": n_sus,
+                 "seconds": ms_sus * 1e-3 * n_sus, "us_per_pair": ms_sus * 1e3 / B, "clocks": clocks_sus}
+
+    # the dominant kernel timed ALONE (one pair per call, nothing overlapped)
     niso = min(B, 32)
     ctx.profile_begin(niso)
     for k in range(niso):
@@ -323,54 +537,42 @@ def run_b200_arm(a, rank, world, local_rank):
     es1.record(stream)
     torch.cuda.synchronize()
     single_us = es0.elapsed_time(es1) * 1e3 / nsp
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    mde_step = B * W * H * D
-    value = world * mde_step * a.steps / (ms * 1e-3) / 1e6
 
-    # ---- end to end through the C ABI with host buffers ----------------------------------
+    # ---- end to end through the C ABI with host buffers -----------------------------------------------------
+    # sm_run_batch: pinned host u8 images -> H2D -> edges -> hot path -> D2H web, a three-stage pipeline.  The web
+    # comes back in the compact u8 format the ABI offers for num_shifts <= 255 (values 1..64 here); the i32 format
+    # (the reference's in-memory type, four times the D2H bytes) is timed alongside.
     Be = min(B, a.e2e_pairs)
     hin1, hin2 = smb.PinnedBuffer((Be, H, W), np.uint8), smb.PinnedBuffer((Be, H, W), np.uint8)
+    hweb8 = smb.PinnedBuffer((Be, H, W), np.uint8)
     hweb = smb.PinnedBuffer((Be, H, W), np.int32)
     for k in range(Be):
         hin1.array[k], hin2.array[k] = pairs[k % distinct][0], pairs[k % distinct][1]
     ectx = smb.StereoContext(W, H, D, SW, variant, device=local_rank, kernel=a.kernel)
-    for _ in range(2):
-        ectx.run_batch(hin1.array, hin2.array, THRESHOLD, web_out=hweb.array)
     e2e_steps = max(3, min(a.steps, 10))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ectx.run_batch(hin1.array, hin2.array, THRESHOLD, web_out=hweb.array)
-    barrier()
-    te = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([te], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        te = float(t.item())
-    e2e_val = world * Be * W * H * D * e2e_steps / te / 1e6
-    e2e_ok = bool(np.array_equal(hweb.array[0], web[0].cpu().numpy()))
-    # the same call with the compact result the ABI offers for num_shifts <= 255 (u8 web: a quarter of the D2H bytes)
-    hweb8 = smb.PinnedBuffer((Be, H, W), np.uint8)
-    ectx.run_batch(hin1.array, hin2.array, THRESHOLD, web_u8=True, web_out=hweb8.array)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ectx.run_batch(hin1.array, hin2.array, THRESHOLD, web_u8=True, web_out=hweb8.array)
-    barrier()
-    te8 = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([te8], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        te8 = float(t.item())
-    e2e8_val = world * Be * W * H * D * e2e_steps / te8 / 1e6
-    e2e8_ok = bool(np.array_equal(hweb8.array[0], hweb.array[0].astype(np.uint8)))
+
+    def time_e2e(u8):
+        out = hweb8.array if u8 else hweb.array
+        for _ in range(2):
+            ectx.run_batch(hin1.array, hin2.array, THRESHOLD, web_u8=u8, web_out=out)
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ectx.run_batch(hin1.array, hin2.array, THRESHOLD, web_u8=u8, web_out=out)
+        env.barrier()
+        te = env.rmax(time.perf_counter() - t0)
+        return world * Be * W * H * D * e2e_steps / te / 1e6, ectx.last_launches()
+
+    e2e8_val, e2e_launches = time_e2e(True)
+    e2e_val, _ = time_e2e(False)
+    parity["e2e_webs_checked"] = check_webs(lambda k: hweb8.array[k].astype(np.int32), Be, "e2e (u8 web)")
+    parity["e2e_i32_webs_checked"] = check_webs(lambda k: hweb.array[k], Be, "e2e (i32 web)")
     # the link's own ceiling for those two calls: pinned host<->device copies, both directions at once
     h2d_gbs, d2h_gbs = benchlib.measure_copy_peak(local_rank, 2)
-    # clocks: every sample taken between the start of the device-timed region and the end of the e2e one
-    clocks = sampler.stop(tw0, time.perf_counter()) if sampler else None
+
+    # ---- the other sharded configs north_star names, same process, after the headline legs ---------------------
+    c4 = leg_config4_pairs(env, smb, a.variant) if not a.no_extra else None
+    c3 = leg_config3_bands(env, smb, a.variant) if not a.no_extra else None
 
     if rank == 0:
         # ---- roofline of the dominant kernel ------------------------------------------------
@@ -382,45 +584,56 @@ def run_b200_arm(a, rank, world, local_rank):
         hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md)"
         if os.path.exists(mp_path):
             hbm_peak, hbm_src = float(json.load(open(mp_path))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
-        traffic, prof = None, {}
+        prof = {}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             prof = json.load(open(tp))
-            traffic = prof.get("main_kernel_dram_bytes_per_launch")
-        # executed (not algorithmic) instruction rate: warp instructions per pair as counted by ncu for the timed
-        # region's launch shape (profiles/) x 32 threads / the per-pair time measured live here
-        issue = None
+        traffic = prof.get("main_kernel_dram_bytes_per_pair")
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        # executed (not algorithmic) work: thread instructions per pair as counted by ncu for the timed region's
+        # launch shape (profiles/traffic.json, refreshed per round) / the per-pair time measured live here
+        issue = alu_mix = None
         bl = prof.get("batched_launch")
-        if bl and a.kernel in (0, 2):
-            tinstr = bl["warp_instructions"] * 32.0 / bl["pairs"]
-            rate = tinstr / (ms * 1e-3 / a.steps / B) / 1e12
-            issue = {"executed_thread_instr_per_pair": tinstr, "achieved": rate, "peak": peak / 1e3, "unit": "T thread-instr/s",
-                     "frac": rate / (peak / 1e3), "alu_pipe_pct_ncu": bl["alu_pipe_pct_of_peak_active"],
-                     "note": "instruction count and ALU-pipe utilisation from ncu (profiles/r01_final_ncu_full_summary.md), "
-                             "time from this run's timed region; the kernel executes about 2.5 thread instructions per "
-                             "pixel x shift where the algorithmic count assumes 8, hence roofline.frac > 1"}
-        achieved = OPS_PER_MDE * W * H * D / main_s / 1e12
+        if bl and "warp_instructions_per_pair" in bl and a.kernel in (0, 2):
+            tinstr = bl["warp_instructions_per_pair"] * 32.0
+            rate = tinstr / (us_pair_tp * 1e-6) / 1e12
+            issue = {"executed_thread_instr_per_pair": tinstr, "achieved": rate, "unit": "T thread-instr/s",
+                     "peak": n_sms * 128 * sm_mhz * 1e6 / 1e12, "frac": rate / (n_sms * 128 * sm_mhz * 1e6 / 1e12),
+                     "peak_how": "SMs x 4 schedulers x 32 lanes x SM clock under load (one warp instruction per "
+                                 "scheduler and cycle)", "source": bl.get("source")}
+            alu_rate = bl["alu_pipe_warp_instructions_per_pair"] * 32.0 / (us_pair_tp * 1e-6) / 1e12
+            alu_mix = {"achieved": alu_rate, "peak": n_sms * 64 * sm_mhz * 1e6 / 1e12, "unit": "T thread-instr/s",
+                       "frac": alu_rate / (n_sms * 64 * sm_mhz * 1e6 / 1e12),
+                       "what": "executed ALU-pipe (LOP3/SHF/IADD3/SEL/ISETP...) thread instructions per second / "
+                               "(SMs x 64 lanes x SM clock): the pipe that binds this kernel; counts from the ncu "
+                               "opcode table of the throughput launch, time from this run's timed region",
+                       "alu_pipe_pct_ncu": bl.get("alu_pipe_pct_of_peak_active")}
+        ach_iso = OPS_PER_MDE * W * H * D / main_s / 1e12
+        ach_tp = OPS_PER_MDE * W * H * D / (us_pair_tp * 1e-6) / 1e12
         roofline = {
-            "bound": "int_alu", "kernel": "bit-sliced match/box/WTA" if ctx.last_launches() else None,
-            "achieved": achieved, "peak": peak / 1e3, "unit": "Tiop/s", "frac": achieved / (peak / 1e3),
-            "traffic": traffic, "issue": issue,
-            "peak_source": "measured live on this GPU: sm_measure_int_peak, max over instruction mixes %s "
+            "bound": "int_alu", "kernel": "k_bitslice (bit-sliced match/box/WTA, window ring in tensor memory)",
+            "achieved": ach_tp, "peak": peak / 1e3, "unit": "Tiop/s", "frac": ach_tp / (peak / 1e3),
+            "frac_throughput": ach_tp / (peak / 1e3), "frac_isolated": ach_iso / (peak / 1e3),
+            "durations": {"throughput_us_per_pair": us_pair_tp, "isolated_us_per_launch": main_s * 1e6,
+                          "what": "throughput: timed region / pairs (launches of consecutive groups overlap on two "
+                                  "streams); isolated: CUDA events around each of %d one-pair launches, nothing overlapped"
+                                  % n_iso},
+            "traffic": traffic, "issue": issue, "alu_mix": alu_mix,
+            "peak_source": "measured live on this GPU (benchlib/peaks.cu), max over instruction mixes %s "
                            "(1e9 thread-instr/s)" % json.dumps({k: round(v) for k, v in peaks.items()}),
-            "algorithmic_ops": "%d int ops per pixel x shift (SURVEY 8d) x %d per launch" % (OPS_PER_MDE, W * H * D),
-            "main_kernel_us": main_s * 1e6, "pack_kernel_us": pack_ms * 1e3 / max(n_iso, 1),
-            "timing": "main/pack kernel durations: CUDA events around each launch, one pair per call, nothing "
-                      "overlapped (%d launches right after the timed region)" % n_iso,
-            "effective_us_per_pair_in_timed_region": ms * 1e3 / a.steps / B,
-            "overlapped_launch_us_in_timed_region": overl_ms * 1e3 / max(n_calls, 1),
-            "note": "in the timed region main kernels of consecutive pairs alternate two streams and the pack "
-                    "kernel runs on a third, so launches overlap and the per-pair time is below the isolated "
-                    "kernel duration; frac uses the isolated duration",
-            "hbm": {"achieved": BYTES_PER_PIXEL * W * H / main_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": BYTES_PER_PIXEL * W * H / main_s / 1e9 / hbm_peak, "source": hbm_src,
-                    "bytes_per_launch": BYTES_PER_PIXEL * W * H},
+            "algorithmic_ops": "%d int ops per pixel x shift (SURVEY 8d) x %d per pair; the kernel is bit-sliced (32 "
+                               "shifts per LOP3) and executes about 2.4 thread instructions per pixel x shift, so "
+                               "frac > 1 is expected: alu_mix and issue are the utilisation figures" % (OPS_PER_MDE, W * H * D),
+            "pack_kernel_us": pack_ms * 1e3 / max(n_iso, 1),
+            "hbm": {"achieved": BYTES_PER_PIXEL * W * H / (us_pair_tp * 1e-6) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": BYTES_PER_PIXEL * W * H / (us_pair_tp * 1e-6) / 1e9 / hbm_peak, "source": hbm_src,
+                    "bytes_per_pair": BYTES_PER_PIXEL * W * H, "duration": "throughput_us_per_pair"},
         }
         cpu = cpu_baseline_single_core() if world == 1 and not a.no_cpu else None
         refcuda = whole_algorithm_baselines(pairs[0], a.variant) if world == 1 and not a.no_cpu else None
+        ceil8 = world * W * H * D / max(2 * W * H / (h2d_gbs * 1e9), W * H / (d2h_gbs * 1e9)) / 1e6
+        ceil32 = world * W * H * D / max(2 * W * H / (h2d_gbs * 1e9), 4 * W * H / (d2h_gbs * 1e9)) / 1e6
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "MDE/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
@@ -430,33 +643,32 @@ def run_b200_arm(a, rank, world, local_rank):
                        "distinct_pairs": distinct, "frames_per_s": value * 1e6 / (W * H * D),
                        "l2": "every pair has its own input and output buffers: %.1f GB per step, far above the "
                              "126 MB L2" % (B * BYTES_PER_PIXEL * W * H / 1e9),
-                       "parallelism": "whole pairs per GPU, no collective", "host_binding_rank0": numa,
+                       "parallelism": "whole pairs per GPU, no collective", "host_binding_rank0": binding,
                        "one_pair_per_call": {"hot_path_us": single_us, "MDE_per_s": W * H * D / single_us,
                                              "what": "sm_match_wta_dev per pair (pack + dependent main kernel), %d calls "
                                                      "back to back on one stream, every pair in its own (cache-cold) buffers, rank 0" % nsp}},
-            "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": e2e_val, "unit": "MDE/s", "h2d_bytes_per_step": 2 * Be * W * H,
-                    "d2h_bytes_per_step": 4 * Be * W * H, "pairs_per_step": Be, "steps": e2e_steps,
-                    "api": "sm_run_batch: pinned host u8 images -> H2D -> edges -> hot path -> D2H i32 web",
-                    "timer": "host wall clock around synchronised API calls", "matches_resident_result": e2e_ok,
-                    "frames_per_s": e2e_val * 1e6 / (W * H * D),
+            "clocks": clocks, "gpu_launches": launches, "sustained": sustained,
+            "e2e": {"value": e2e8_val, "unit": "MDE/s", "h2d_bytes_per_step": 2 * Be * W * H,
+                    "d2h_bytes_per_step": Be * W * H, "pairs_per_step": Be, "steps": e2e_steps,
+                    "api": "sm_run_batch(web_u8=1): pinned host u8 images -> H2D -> edges+planes -> hot path -> D2H u8 web "
+                           "(values 1..64; the compact result format of the ABI for num_shifts <= 255)",
+                    "timer": "host wall clock around synchronised API calls, max over ranks",
+                    "frames_per_s": e2e8_val * 1e6 / (W * H * D), "gpu_launches_per_step": e2e_launches,
                     "link": {"h2d_GBps": h2d_gbs, "d2h_GBps": d2h_gbs,
-                             "how": "sm_measure_copy_peak: 256 MB pinned copies, both directions at once, best of 3",
-                             "ceiling_MDE_per_s": world * W * H * D / max(2 * W * H / (h2d_gbs * 1e9),
-                                                                          4 * W * H / (d2h_gbs * 1e9)) / 1e6,
-                             "ceiling_with_u8_web_MDE_per_s": world * W * H * D / max(2 * W * H / (h2d_gbs * 1e9),
-                                                                                      W * H / (d2h_gbs * 1e9)) / 1e6,
-                             "note": "per pair 2 u8 images go up and one i32 (or u8) web comes down; the slower "
-                                     "direction bounds pairs/s, compute overlaps"},
-                    "with_u8_web": {"value": e2e8_val, "unit": "MDE/s", "d2h_bytes_per_step": Be * W * H,
-                                    "equal_to_i32_web": e2e8_ok,
-                                    "note": "sm_run_batch(web_u8=1): same values, one byte per pixel"}},
+                             "how": "benchlib: 256 MB pinned copies, both directions at once, best of 3 (rank 0)",
+                             "ceiling_MDE_per_s": ceil8, "frac_of_ceiling": e2e8_val / ceil8,
+                             "note": "per pair 2 u8 images go up and one u8 web comes down; the slower direction "
+                                     "bounds pairs/s, compute overlaps"},
+                    "with_i32_web": {"value": e2e_val, "unit": "MDE/s", "d2h_bytes_per_step": 4 * Be * W * H,
+                                     "ceiling_MDE_per_s": ceil32, "frac_of_ceiling": e2e_val / ceil32,
+                                     "note": "sm_run_batch(web_u8=0): the reference's in-memory type (int *web, "
+                                             "stereo.c:196); same values, four bytes per pixel over the link"}},
             "roofline": roofline, "cpu_baseline": cpu, "reference_cuda_baseline": refcuda, "parity": parity,
+            "config4_pairs": c4, "config3_bands": c3,
         }), flush=True)
     hin1.free(), hin2.free(), hweb.free(), hweb8.free()
     ctx.close(), ectx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    env.close()
 
 
 def main():
@@ -472,6 +684,7 @@ def main():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 direct, 2 bit-sliced")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-overlap", action="store_true", help="one sm_match_wta_dev call per pair (pack not overlapped)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config4_pairs / config3_bands legs")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -15,6 +15,10 @@
  *     helper_cuda.h:890-905): the library only returns codes, the policy lives here.
  *
  * Build: -DSM_VARIANT=0 -> stereopar (wrap-around), -DSM_VARIANT=1 -> stereopar-ghost.
+ * -DREF_HOST (oracle/Makefile, target refhost): the host side is the REFERENCE'S OWN -- src/image.c with the
+ * vendored stb_image.h loader, Image.data as double, its write_image and util.h -- compiled where it lies;
+ * the images then go up through sm_upload_f64 in the reference's double layout.  That build proves the
+ * boundary of INTEGRATION.md section 2 with the reference's loader and writer instead of host/hostimage.c.
  * NUM_SHIFTS is the reference's compile-time constant (stereo.cu:6); here it can also be
  * set at run time with the environment variable STEREO_NUM_SHIFTS.
  */
@@ -23,7 +27,17 @@
 #include <string.h>
 #include <time.h>
 
+#ifdef REF_HOST
+#include "image.h" /* the reference's (-I<reference>/src): Image, read_image, make_filename, write_image; brings util.h */
+typedef Image HostImage;
+#define WRITE_IMAGE(data, w, h, type, file) write_image((void *)(data), (w), (h), 0, (type), (file))
+#define UPLOAD(ctx, a, b) sm_upload_f64((ctx), (a).data, (b).data) /* Image.data: double = u8/256.0, image.c:13 */
+#else
 #include "hostimage.h"
+typedef Image8 HostImage;
+#define WRITE_IMAGE(data, w, h, type, file) write_image((data), (w), (h), (type), (file))
+#define UPLOAD(ctx, a, b) sm_upload_u8((ctx), (a).data, (b).data)
+#endif
 #include "stereo_b200.h"
 
 #ifndef SM_VARIANT
@@ -39,6 +53,7 @@
 
 #define PROGRAM_TYPE (SM_VARIANT == 0 ? PAR : PARGHOST)
 
+#ifndef REF_HOST /* util.h of the reference has its own get_time, xmalloc and parse_* (util.h:49-75,104-109) */
 static double get_time(void)
 {
     struct timespec ts;
@@ -73,6 +88,7 @@ static int parse_int(const char *s, int *n)
     *n = (int)strtol(s, &end, 0);
     return *n == 0 && end == s;
 }
+#endif /* !REF_HOST */
 
 /* checkCudaErrors' policy (helper_cuda.h:890-905): report and stop */
 #define CHECK(call)                                                                            \
@@ -96,7 +112,7 @@ static void dump(sm_ctx *ctx, int which, int shift, void *host, int w, int h, Im
                  int number)
 {
     CHECK(sm_download(ctx, which, shift, host));
-    write_image(host, w, h, type, make_filename(name, PROGRAM_TYPE, number));
+    WRITE_IMAGE(host, w, h, type, make_filename(name, PROGRAM_TYPE, number));
 }
 #endif
 
@@ -165,7 +181,7 @@ int main(int argc, char *argv[])
         return 1;
     }
 
-    Image8 first, second;
+    HostImage first, second;
     if (read_image(argv[1], &first)) return 1;
     if (read_image(argv[2], &second)) return 1;
     if (first.width != second.width || first.height != second.height) {
@@ -216,7 +232,7 @@ int main(int argc, char *argv[])
     sm_ctx *ctx = NULL;
     CHECK(sm_create(&ctx, 0, first.width, first.height, num_shifts, params.square_width,
                     SM_VARIANT == 0 ? SM_WRAP : SM_GHOST));
-    CHECK(sm_upload_u8(ctx, first.data, second.data));
+    CHECK(UPLOAD(ctx, first, second));
     CHECK(sm_synchronize(ctx));
 
     algorithm(ctx, first.width, first.height, num_shifts, params);

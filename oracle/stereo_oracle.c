@@ -251,7 +251,11 @@ void oracle_fill_web_holes(int32_t *web, int w, int h, int times)
             for (int x = 0; x < w; x++) {
                 size_t p = (size_t)y * w + x;
                 if (b[p] == 0) {
-                    int32_t r = x + 1 < w ? b[p + 1] : 0, l = x > 0 ? b[p - 1] : 0;
+                    /* the reference indexes with the UNWRAPPED IDX(x+-1, y) (stereo.c:237-243): at a row end the
+                     * "right" neighbour is the first pixel of the next row and vice versa.  Only the reads that
+                     * leave the array altogether (first/last pixel, rows above the first and below the last) are
+                     * undefined there; they count as 0 here. */
+                    int32_t r = p + 1 < n ? b[p + 1] : 0, l = p > 0 ? b[p - 1] : 0;
                     int32_t u = y + 1 < h ? b[p + w] : 0, d = y > 0 ? b[p - w] : 0;
                     a[p] = (r + u + l + d) / 4;
                 }

@@ -226,6 +226,138 @@ k_edges_lut(const uint8_t *__restrict__ img, int W, int FH, int ystart, int nrow
     *reinterpret_cast<uint32_t *>(edges + (size_t)y * W + x4) = out;
 }
 
+// ---- edges straight into the packed planes ---------------------------------------------------
+// The whole-algorithm and batch paths never need the byte edge maps: this kernel detects the edges of BOTH
+// images of a pair over the PADDED band (rows [row0-half, row1+half), columns [-PADL, WPR*32-PADL)) and writes
+// the three 1-bit planes LA / LB / RB of sm_common.cuh directly, with the border policy of the variant applied
+// to the coordinates (a padding pixel of the WRAP variant IS the wrapped image pixel; GHOST padding is zero and
+// invalid).  It stands in for k_edges_lut + k_pack: one launch and 4 B per pixel of traffic less.  Thread =
+// 4 consecutive pixels of one image; eight threads' nibbles are OR-reduced into a 32-pixel word by shuffles.
+// WRITE_U8: also store the byte maps (in-image pixels only), for sm_download(SM_EDGES*) and the debug planes.
+template <int VARIANT, bool WRITE_U8>
+__global__ void __launch_bounds__(128)
+k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img2, int FH, int row0, PackedGeom g,
+               double thr, const uint32_t *__restrict__ lut, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB,
+               uint32_t *__restrict__ RB, uint8_t *__restrict__ edges1, uint8_t *__restrict__ edges2, size_t image_stride,
+               size_t plane_stride)
+{
+    // the hot kernel may be scheduled as this grid's programmatic dependent (it waits for completion before
+    // it reads the planes)
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int pair = blockIdx.z >> 1, side = blockIdx.z & 1;
+    const uint8_t *img = (side ? img2 : img1) + (size_t)pair * image_stride;
+    uint8_t *edges = WRITE_U8 ? (side ? edges2 : edges1) + (size_t)pair * image_stride : nullptr;
+    const int W = g.W;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // thread <-> 4 pixels; 8 threads <-> one word
+    const int wd = t >> 3;
+    const int lane = threadIdx.x & 31;
+    const int pr = blockIdx.y;
+    int y = row0 - g.half + pr;
+    bool rowvalid = true;
+    if (VARIANT == SM_WRAP) {
+        y %= FH;
+        if (y < 0) y += FH;
+    } else {
+        rowvalid = y >= 0 && y < FH;
+    }
+    const int x4 = t * 4 - PADL;
+    uint32_t e = 0, v = 0;
+    if (wd < g.WPR && rowvalid) {
+        int ym = y - 1, yp = y + 1;
+        if (VARIANT == SM_WRAP) {
+            ym = ym < 0 ? ym + FH : ym;
+            yp = yp >= FH ? yp - FH : yp;
+        }
+        const bool fast = ym >= 0 && yp < FH && (W & 3) == 0 && x4 >= 4 && x4 + 8 <= W &&
+                          (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+        if (fast) {
+            int p[3][6];  // pixels x4-1 .. x4+4 of the three rows
+            const int ys[3] = {ym, y, yp};
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(img + (size_t)ys[j] * W + x4);
+                const uint32_t a = __ldg(w - 1), b = __ldg(w), c = __ldg(w + 1);
+                p[j][0] = a >> 24;
+                p[j][1] = b & 255, p[j][2] = (b >> 8) & 255, p[j][3] = (b >> 16) & 255, p[j][4] = b >> 24;
+                p[j][5] = c & 255;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int tl = p[0][k], tc = p[0][k + 1], tr = p[0][k + 2];
+                const int ml = p[1][k], mr = p[1][k + 2];
+                const int bl = p[2][k], bc = p[2][k + 1], br = p[2][k + 2];
+                const int b = lut_bit(lut, tl + ml + bl, tr + mr + br) | lut_bit(lut, tl + tc + tr, bl + bc + br) |
+                              lut_bit(lut, tl + tc + ml, mr + bc + br) | lut_bit(lut, bl + bc + ml, tc + tr + mr);
+                e |= (uint32_t)b << k;
+            }
+            v = 0xFu;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int x = x4 + k;
+                bool ok = true;
+                if (VARIANT == SM_WRAP) {
+                    x %= W;
+                    if (x < 0) x += W;
+                } else {
+                    ok = x >= 0 && x < W;
+                }
+                if (ok) {
+                    e |= (uint32_t)edge_pixel<VARIANT>(img, W, FH, x, y, thr, lut) << k;
+                    v |= 1u << k;
+                }
+            }
+        }
+        if (WRITE_U8) {
+            // the byte maps hold the frame itself: only the unwrapped in-image pixels of this word
+            if (x4 >= 0 && x4 + 4 <= W && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(edges) & 3) == 0) {
+                *reinterpret_cast<uint32_t *>(edges + (size_t)y * W + x4) =
+                    (e & 1u) | ((e & 2u) << 7) | ((e & 4u) << 14) | ((e & 8u) << 21);
+            } else {
+                for (int k = 0; k < 4; k++)
+                    if (x4 + k >= 0 && x4 + k < W) edges[(size_t)y * W + x4 + k] = (uint8_t)((e >> k) & 1u);
+            }
+        }
+    }
+    // eight threads' nibbles -> one 32-pixel word (all 32 lanes take part)
+    const int sh = 4 * (lane & 7);
+    uint32_t ew = e << sh, vw = v << sh;
+#pragma unroll
+    for (int m = 1; m <= 4; m <<= 1) {
+        ew |= __shfl_xor_sync(0xFFFFFFFFu, ew, m);
+        vw |= __shfl_xor_sync(0xFFFFFFFFu, vw, m);
+    }
+    if ((lane & 7) == 0 && wd < g.WPR) {
+        const size_t o = (size_t)pair * plane_stride + (size_t)pr * g.WPR + wd;
+        if (side == 0) {
+            LA[o] = ew & vw;
+            LB[o] = ~ew & vw;
+        } else {
+            RB[o] = ew & vw;
+        }
+    }
+}
+
+int launch_edges_planes(const uint8_t *img1, const uint8_t *img2, int FH, int row0, int variant, const PackedGeom &g,
+                        double threshold, const uint32_t *lut, uint32_t *LA, uint32_t *LB, uint32_t *RB, uint8_t *edges1,
+                        uint8_t *edges2, cudaStream_t s, int npairs, size_t image_stride, size_t plane_stride)
+{
+    dim3 block(128);
+    dim3 grid((g.WPR * 8 + block.x - 1) / block.x, g.ER, 2 * npairs);
+    const bool u8 = edges1 != nullptr && edges2 != nullptr;
+#define SM_EP(V, U) \
+    k_edges_planes<V, U><<<grid, block, 0, s>>>(img1, img2, FH, row0, g, threshold, lut, LA, LB, RB, edges1, edges2, \
+                                                image_stride, plane_stride)
+    if (variant == SM_WRAP) {
+        if (u8) SM_EP(SM_WRAP, true); else SM_EP(SM_WRAP, false);
+    } else {
+        if (u8) SM_EP(SM_GHOST, true); else SM_EP(SM_GHOST, false);
+    }
+#undef SM_EP
+    SM_CUDA(cudaGetLastError());
+    return 1;
+}
+
 int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s)
 {
     k_edge_lut<<<LUT_N, 32, 0, s>>>(threshold, lut);
@@ -255,7 +387,11 @@ void warm_edges(int variant)
         warm_kernel(k_edges<uint8_t, SM_WRAP>);
         warm_kernel(k_edges<double, SM_WRAP>);
         warm_kernel(k_edges_lut<SM_WRAP>);
+        warm_kernel(k_edges_planes<SM_WRAP, true>);
+        warm_kernel(k_edges_planes<SM_WRAP, false>);
     } else {
+        warm_kernel(k_edges_planes<SM_GHOST, true>);
+        warm_kernel(k_edges_planes<SM_GHOST, false>);
         warm_kernel(k_edges<uint8_t, SM_GHOST>);
         warm_kernel(k_edges<double, SM_GHOST>);
         warm_kernel(k_edges_lut<SM_GHOST>);

@@ -12,8 +12,10 @@
 namespace smb {
 
 // web is never 0 after step 2 (every pixel gets some i+1), so the branch body never
-// runs on real data.  The reference reads the four neighbours without
-// bounds checks (stereo.cu:240-243); out-of-frame neighbours are taken as 0 here.
+// runs on real data.  The reference reads the four neighbours with the unwrapped
+// IDX(x+-1, y) and without bounds checks (stereo.cu:240-243): at a row end the right neighbour is the
+// first pixel of the next row (and vice versa).  That is kept; only reads that leave the array
+// altogether (undefined in the reference) count as 0.
 __global__ void __launch_bounds__(256)
 k_fill_holes(const int32_t *__restrict__ src, int32_t *__restrict__ dst, int W, int H)
 {
@@ -22,7 +24,7 @@ k_fill_holes(const int32_t *__restrict__ src, int32_t *__restrict__ dst, int W, 
     if (x >= W || y >= H) return;
     size_t p = (size_t)y * W + x;
     if (src[p] == 0) {
-        int32_t r = x + 1 < W ? src[p + 1] : 0, l = x > 0 ? src[p - 1] : 0;
+        int32_t r = p + 1 < (size_t)W * H ? src[p + 1] : 0, l = p > 0 ? src[p - 1] : 0;
         int32_t u = y + 1 < H ? src[p + W] : 0, d = y > 0 ? src[p - W] : 0;
         dst[p] = (r + u + l + d) / 4;
     }

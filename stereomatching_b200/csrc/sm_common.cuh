@@ -119,6 +119,11 @@ size_t edge_lut_words();
 int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
                      const uint32_t *lut, uint8_t *edges, cudaStream_t s, int n_images = 1, size_t image_stride = 0);
 
+// both images of npairs pairs -> packed planes in one launch (edges1/edges2 non-NULL: the byte maps as well)
+int launch_edges_planes(const uint8_t *img1, const uint8_t *img2, int FH, int row0, int variant, const PackedGeom &g,
+                        double threshold, const uint32_t *lut, uint32_t *LA, uint32_t *LB, uint32_t *RB, uint8_t *edges1,
+                        uint8_t *edges2, cudaStream_t s, int npairs = 1, size_t image_stride = 0, size_t plane_stride = 0);
+
 int launch_fill_web_holes_step(const int32_t *src, int32_t *dst, int W, int H, cudaStream_t s);
 int launch_minmax(const int32_t *a, size_t n, int32_t *d_minmax, cudaStream_t s);
 int launch_contour(const int32_t *web, size_t n, int32_t mn, int32_t interval, uint8_t *out,

@@ -56,6 +56,7 @@ struct sm_ctx {
     int img_kind = 0;  // 0 none, 1 u8, 2 f64
     uint8_t *edges[2] = {nullptr, nullptr};
     bool have_edges = false;
+    bool planes_valid = false;  // LA/LB/RB already hold the packed planes of edges[] (sm_edges wrote them itself)
     uint32_t *edge_lut = nullptr;  // detector decisions for all (L, R) sum pairs at lut_threshold
     double lut_threshold = -1.0;
     bool edges_fp64_only = false;  // SM_OPT_EDGES_FP64: always take the FP64 kernel (cross-check)
@@ -235,9 +236,13 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
     cudaEvent_t *pe = (c->prof_ev && c->prof_n < c->prof_cap) ? c->prof_ev + 3 * c->prof_n : nullptr;
     SM_CUDA(cudaEventRecord(c->ev0, c->stream));
     if (pe) SM_CUDA(cudaEventRecord(pe[0], c->stream));
-    rc = launch_pack(e1, e2, c->FH, c->row0, c->variant, c->g, c->LA, c->LB, c->RB, c->stream);
-    if (rc < 0) return rc;
-    launches += rc;
+    // sm_edges writes the packed planes itself (k_edges_planes): no pack launch then
+    const bool packed = c->planes_valid && e1 == c->edges[0] && e2 == c->edges[1];
+    if (!packed) {
+        rc = launch_pack(e1, e2, c->FH, c->row0, c->variant, c->g, c->LA, c->LB, c->RB, c->stream);
+        if (rc < 0) return rc;
+        launches += rc;
+    }
     if (pe) SM_CUDA(cudaEventRecord(pe[1], c->stream));
     HotArgs a = hot_args(c, best, web);
 #ifdef SMB_DEV
@@ -245,7 +250,10 @@ int run_hot(sm_ctx *c, const uint8_t *e1, const uint8_t *e2, int32_t *best, int3
 #else
     constexpr bool no_pdl = false;
 #endif
-    a.after_pack = pe == nullptr && !no_pdl;  // nothing lies between the two launches unless the per-kernel profile is on
+    // the producer of the planes (pack or edge kernel) is the launch just before on this stream unless the
+    // per-kernel profile put an event in between: the main kernel may start as its programmatic dependent.
+    // (It waits for every earlier grid of the stream to complete before it reads anything, whatever that grid is.)
+    a.after_pack = pe == nullptr && !no_pdl;
     rc = launch_main(c, a, c->stream);
     if (rc < 0) return rc;
     launches += rc;
@@ -551,10 +559,14 @@ extern "C" int sm_edges(sm_ctx *c, double threshold)
         if ((rc = launch_edge_lut(threshold, c->edge_lut, c->stream)) < 0) return rc;
         c->lut_threshold = threshold;
     }
-    if (use_lut) {  // both images in one launch: they sit npix apart in one allocation
-        int rc = launch_edges_lut(c->img_u8[0], c->W, c->FH, ystart, nrows, c->variant, threshold, c->edge_lut,
-                                  c->edges[0], c->stream, 2, c->npix());
+    c->planes_valid = false;
+    if (use_lut) {
+        // both images in one launch, straight into the packed planes of the hot path; the byte maps are written
+        // as well (sm_download(SM_EDGES*), debug planes)
+        int rc = launch_edges_planes(c->img_u8[0], c->img_u8[1], c->FH, c->row0, c->variant, c->g, threshold, c->edge_lut,
+                                     c->LA, c->LB, c->RB, c->edges[0], c->edges[1], c->stream);
         if (rc < 0) return rc;
+        c->planes_valid = true;
     } else {
         for (int k = 0; k < 2; k++) {
             int rc;
@@ -579,6 +591,7 @@ extern "C" int sm_set_edges(sm_ctx *c, const uint8_t *first_edges, const uint8_t
     if ((rc = copy_rows_h2d(c, c->edges[0], first_edges, c->row0 - c->half, c->row1 + c->half)) ||
         (rc = copy_rows_h2d(c, c->edges[1], second_edges, c->row0 - c->half, c->row1 + c->half)))
         return rc;
+    c->planes_valid = false;
     c->have_edges = true;
     return SM_OK;
 }
@@ -608,14 +621,13 @@ extern "C" int sm_match_wta_dev(sm_ctx *c, const uint8_t *d_first_edges, const u
     return run_hot(c, d_first_edges, d_second_edges, d_best, d_web);
 }
 
-extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_first_edges,
-                                      const uint8_t *d_second_edges, size_t edge_stride, int32_t *d_best,
-                                      int32_t *d_web, size_t out_stride)
+// The batched hot path on device-resident inputs: either byte edge maps (packed by k_pack) or, with
+// from_images, the 8-bit images themselves (edges detected straight into the packed planes by k_edges_planes;
+// the byte maps never exist).  Producer launches run on a second stream one group ahead of the main kernels.
+static int batch_core(sm_ctx *c, int n_pairs, bool from_images, double threshold, const uint8_t *d_first_edges,
+                      const uint8_t *d_second_edges, size_t edge_stride, int32_t *d_best, int32_t *d_web,
+                      size_t out_stride)
 {
-    SM_ENTER(c);
-    SM_REQUIRE(n_pairs >= 0 && d_first_edges && d_second_edges && d_best && d_web,
-               "sm_match_wta_dev_batch: bad arguments");
-    SM_REQUIRE(edge_stride >= c->npix() && out_stride >= c->npix(), "sm_match_wta_dev_batch: stride below frame size");
     constexpr int NPB = sm_ctx::NPB;
     const size_t pw = (size_t)c->g.ER * c->g.WPR;
     int kk = c->kernel;
@@ -665,9 +677,14 @@ extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_f
         const int b = group % NPB;
         int rc;
         if (group >= NPB) SM_CUDA(cudaStreamWaitEvent(c->pack_stream, c->ev_used[b], 0));  // set b is free again
-        rc = launch_pack(d_first_edges + (size_t)k * edge_stride, d_second_edges + (size_t)k * edge_stride, c->FH,
-                         c->row0, c->variant, c->g, c->pLA[b], c->pLB[b], c->pRB[b], c->pack_stream, np,
-                         edge_stride, pw);
+        if (from_images)
+            rc = launch_edges_planes(d_first_edges + (size_t)k * edge_stride, d_second_edges + (size_t)k * edge_stride,
+                                     c->FH, c->row0, c->variant, c->g, threshold, c->edge_lut, c->pLA[b], c->pLB[b],
+                                     c->pRB[b], nullptr, nullptr, c->pack_stream, np, edge_stride, pw);
+        else
+            rc = launch_pack(d_first_edges + (size_t)k * edge_stride, d_second_edges + (size_t)k * edge_stride, c->FH,
+                             c->row0, c->variant, c->g, c->pLA[b], c->pLB[b], c->pRB[b], c->pack_stream, np,
+                             edge_stride, pw);
         if (rc < 0) return rc;
         launches += rc;
         SM_CUDA(cudaEventRecord(c->ev_packed[b], c->pack_stream));
@@ -703,6 +720,17 @@ extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_f
     c->timed = true;
     c->last_launches = launches;
     return SM_OK;
+}
+
+extern "C" int sm_match_wta_dev_batch(sm_ctx *c, int n_pairs, const uint8_t *d_first_edges,
+                                      const uint8_t *d_second_edges, size_t edge_stride, int32_t *d_best,
+                                      int32_t *d_web, size_t out_stride)
+{
+    SM_ENTER(c);
+    SM_REQUIRE(n_pairs >= 0 && d_first_edges && d_second_edges && d_best && d_web,
+               "sm_match_wta_dev_batch: bad arguments");
+    SM_REQUIRE(edge_stride >= c->npix() && out_stride >= c->npix(), "sm_match_wta_dev_batch: stride below frame size");
+    return batch_core(c, n_pairs, false, 0.0, d_first_edges, d_second_edges, edge_stride, d_best, d_web, out_stride);
 }
 
 extern "C" int sm_elapsed_ms(sm_ctx *c, float *ms)
@@ -949,8 +977,8 @@ extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const 
         if (!P.up) SM_CUDA(cudaStreamCreateWithFlags(&P.up, cudaStreamNonBlocking));
         if (!P.down) SM_CUDA(cudaStreamCreateWithFlags(&P.down, cudaStreamNonBlocking));
         for (int k = 0; k < NP; k++) {
-            if ((rc = dev_alloc(&P.img[k], 2 * P.group * n)) || (rc = dev_alloc(&P.edg[k], 2 * P.group * n)) ||
-                (rc = dev_alloc(&P.web[k], P.group * n)) || (rc = dev_alloc(&P.best[k], P.group * n)))
+            if ((rc = dev_alloc(&P.img[k], 2 * P.group * n)) || (rc = dev_alloc(&P.web[k], P.group * n)) ||
+                (rc = dev_alloc(&P.best[k], P.group * n)))
                 return rc;
             if (!P.ev_up[k]) SM_CUDA(cudaEventCreateWithFlags(&P.ev_up[k], cudaEventDisableTiming));
             if (!P.ev_comp[k]) SM_CUDA(cudaEventCreateWithFlags(&P.ev_comp[k], cudaEventDisableTiming));
@@ -962,6 +990,9 @@ extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const 
         for (int k = 0; k < NP; k++)
             if ((rc = dev_alloc(&P.web8[k], P.group * n))) return rc;
     const bool use_lut = !c->edges_fp64_only;
+    if (!use_lut)  // byte edge maps exist only on the FP64 cross-check path
+        for (int k = 0; k < NP; k++)
+            if ((rc = dev_alloc(&P.edg[k], 2 * P.group * n))) return rc;
     if (use_lut && c->lut_threshold != threshold) {
         if ((rc = dev_alloc(&c->edge_lut, edge_lut_words()))) return rc;
         if ((rc = launch_edge_lut(threshold, c->edge_lut, c->stream)) < 0) return rc;
@@ -982,13 +1013,9 @@ extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const 
         // ---- stage 2, the context's stream: edges of all 2*np images, then the batched hot path
         SM_CUDA(cudaStreamWaitEvent(c->stream, P.ev_up[b], 0));
         if (use_lut) {
-            // first and second images sit G images apart: one launch each keeps the z-slices dense
-            for (int side = 0; side < 2; side++) {
-                rc = launch_edges_lut(P.img[b] + (size_t)side * G * n, c->W, c->FH, 0, c->FH, c->variant, threshold,
-                                      c->edge_lut, P.edg[b] + (size_t)side * G * n, c->stream, np, n);
-                if (rc < 0) return rc;
-                launches += rc;
-            }
+            // edges of all 2*np images straight into the packed planes, then the hot path: two kernels per group
+            if ((rc = batch_core(c, np, true, threshold, P.img[b], P.img[b] + (size_t)G * n, n, P.best[b], P.web[b], n)))
+                return rc;
         } else {
             for (int j = 0; j < 2 * G; j++) {
                 if (j % G >= np) continue;
@@ -997,9 +1024,9 @@ extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const 
                 if (rc < 0) return rc;
                 launches += rc;
             }
+            if ((rc = batch_core(c, np, false, 0.0, P.edg[b], P.edg[b] + (size_t)G * n, n, P.best[b], P.web[b], n)))
+                return rc;
         }
-        if ((rc = sm_match_wta_dev_batch(c, np, P.edg[b], P.edg[b] + (size_t)G * n, n, P.best[b], P.web[b], n)))
-            return rc;
         launches += c->last_launches;
         if (web_u8) {
             if ((rc = launch_i32_to_u8(P.web[b], P.web8[b], (size_t)np * n, c->stream)) < 0) return rc;

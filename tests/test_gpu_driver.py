@@ -84,6 +84,32 @@ def test_diff_sh_against_the_reference_serial_programs(workdir):
     assert not problems, problems
 
 
+@pytest.mark.parametrize("fixture", ["1-240x135", "2-480x270", "3-960x540"])
+def test_diff_sh_with_the_reference_host_side(tmp_path, fixture):
+    """INTEGRATION.md section 2 as a real build: host/driver.c compiled with the REFERENCE'S OWN image.c /
+    stb_image.h / util.h (oracle/Makefile refhost), images uploaded in the reference's double layout
+    (sm_upload_f64).  The test/diff.sh loop: all 96 files of par/ and pargh/ byte-equal to ser/ and sergh/ written
+    by the reference's serial programs (src/stereo.cu:350-409, src/image.c:18-88)."""
+    dbg = os.path.join(ROOT, "oracle", "_ref", "debug")
+    opt = os.path.join(ROOT, "oracle", "_ref", "debugopt")
+    exes = {"par": os.path.join(dbg, "stereopar-refhost"), "pargh": os.path.join(dbg, "stereopar-ghost-refhost"),
+            "ser": os.path.join(opt, "stereomatch"), "sergh": os.path.join(opt, "stereomatch-ghost")}
+    if not all(os.path.exists(e) for e in exes.values()):
+        pytest.skip("oracle/_ref refhost / refserialopt not built (needs /root/reference at build time)")
+    for f in ("a.png", "b.png"):
+        shutil.copy(os.path.join(IMGS, fixture, f), tmp_path / f)
+    for sub, exe in exes.items():
+        (tmp_path / sub).mkdir()
+        r = subprocess.run([exe, "a.png", "b.png"], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode == 0, (sub, r.stderr)
+    names = sorted(os.listdir(tmp_path / "ser"))
+    assert names == sorted(NAMES)
+    problems = [(n, x, y) for n in names for x, y in (("ser", "par"), ("sergh", "pargh"))
+                if open(tmp_path / x / n, "rb").read() != open(tmp_path / y / n, "rb").read()]
+    assert not problems, problems[:5]
+    shutil.rmtree(tmp_path, ignore_errors=True)
+
+
 def test_timing_build_writes_nothing(tmp_path):
     for f in ("a.png", "b.png"):
         shutil.copy(os.path.join(IMGS, "2-480x270", f), tmp_path / f)

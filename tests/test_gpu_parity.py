@@ -49,7 +49,7 @@ def test_fixture_end_to_end(golden, name, variant, kernel):
         best, web = c.download(smb.BEST), c.download(smb.WEB)
         assert oracle.crc32(best) == g["best"]
         assert oracle.crc32(web) == g["web"]
-        assert c.last_launches() >= 2 and c.elapsed_ms() > 0.0
+        assert c.last_launches() >= 1 and c.elapsed_ms() > 0.0
 
 
 @pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)

@@ -179,6 +179,27 @@ def test_step3(orc):
     assert f2.shape == web.shape
 
 
+def test_fill_web_holes_equals_reference(orc):
+    """Holes (zeros) at row ends: the reference's unwrapped IDX(x+-1, y) makes the last pixel of a row a neighbour
+    of the first pixel of the next (stereo.c:237-243).  Holes stay away from the first and last rows, where the
+    reference reads outside the array; an even number of passes, so that it returns (and does not free) our buffer."""
+    if not oracle.ref_available(oracle.WRAP, 30):
+        pytest.skip("oracle/_ref not built")
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    w, h = 37, 23
+    web = rng.integers(1, 31, size=(h, w), dtype=np.int32)
+    for (y, x) in [(5, w - 1), (7, 0), (9, w - 1), (10, 0), (12, 18), (12, 19), (13, 18)]:
+        web[y, x] = 0
+    L = oracle.RefLib(oracle.WRAP, 30).L
+    L.fill_web_holes.restype = C.c_void_p
+    for times in (2, 6, 32):
+        ref = np.ascontiguousarray(web.copy())
+        p = L.fill_web_holes(ref.ctypes.data_as(C.c_void_p), w, h, times)
+        assert p == ref.ctypes.data
+        assert np.array_equal(orc.fill_web_holes(web, times), ref), times
+
+
 @pytest.mark.parametrize("variant", [oracle.WRAP, oracle.GHOST])
 def test_oracle_equals_reference_wide_windows(orc, variant):
     """Windows beyond the reference default (23..63): the GPU tests use the oracle as checker there too, so the
