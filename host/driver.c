@@ -15,7 +15,7 @@
  *     helper_cuda.h:890-905): the library only returns codes, the policy lives here.
  *
  * Build: -DSM_VARIANT=0 -> stereopar (wrap-around), -DSM_VARIANT=1 -> stereopar-ghost.
- * -DREF_HOST (oracle/Makefile, target refhost): the host side is the REFERENCE'S OWN -- src/image.c with the
+ * -DREF_HOST (the recipe lives with the test infrastructure, target refhost): the host side is the REFERENCE'S OWN -- src/image.c with the
  * vendored stb_image.h loader, Image.data as double, its write_image and util.h -- compiled where it lies;
  * the images then go up through sm_upload_f64 in the reference's double layout.  That build proves the
  * boundary of INTEGRATION.md section 2 with the reference's loader and writer instead of host/hostimage.c.

@@ -83,6 +83,13 @@ typedef enum sm_option {
                               0 (default): the kernel's cost model */
 } sm_option;
 
+/* What sm_get_info reports about the launch configuration of the bit-sliced kernel on this context. */
+typedef enum sm_info {
+    SM_INFO_WARPS_PER_SM = 1,     /* resident warps per SM of the kernel instantiation this geometry uses */
+    SM_INFO_PAIRS_PER_LAUNCH = 2, /* pairs the batch entries put into one launch (0 before the first batch call) */
+    SM_INFO_TMEM_COLUMNS = 3      /* tensor-memory columns one CTA allocates for the vertical-window ring */
+} sm_info;
+
 /* ---- library-level -------------------------------------------------------- */
 
 /* Message of the last failure on this thread ("" if none). */
@@ -123,6 +130,8 @@ int sm_destroy(sm_ctx *ctx);
 int sm_set_stream(sm_ctx *ctx, void *cuda_stream);
 int sm_set_kernel(sm_ctx *ctx, int kernel);
 int sm_set_option(sm_ctx *ctx, int option, int value);
+/* A non-negative value, or a negative sm_status. */
+int sm_get_info(sm_ctx *ctx, int what);
 int sm_synchronize(sm_ctx *ctx);
 
 /* ---- step 0: upload ------------------------------------------------------- */

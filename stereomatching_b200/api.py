@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("STEREO_B200_LIB") or os.path.join(HERE, "libstereo_b2
 WRAP, GHOST = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_BITSLICE = 0, 1, 2
 OPT_EDGES_FP64, OPT_PIPE_GROUP, OPT_ROW_RUNS = 1, 2, 3
+INFO_WARPS_PER_SM, INFO_PAIRS_PER_LAUNCH, INFO_TMEM_COLUMNS = 1, 2, 3
 (EDGES1, EDGES2, MATCH, SCORE_ALL, SCORE, BEST, WEB, WEB_FILLED, OUTPUT) = range(9)
 _PLANE_DTYPE = {EDGES1: np.uint8, EDGES2: np.uint8, MATCH: np.uint8, SCORE_ALL: np.int32,
                 SCORE: np.int32, BEST: np.int32, WEB: np.int32, WEB_FILLED: np.int32,
@@ -29,7 +30,7 @@ SYMBOLS = [
     "sm_create", "sm_create_band", "sm_destroy", "sm_set_stream", "sm_set_kernel",
     "sm_synchronize", "sm_upload_f64", "sm_upload_u8", "sm_edges", "sm_set_edges",
     "sm_match_wta", "sm_match_wta_dev", "sm_match_wta_dev_batch", "sm_elapsed_ms", "sm_last_launches",
-    "sm_profile_begin", "sm_profile_read", "sm_set_option",
+    "sm_profile_begin", "sm_profile_read", "sm_set_option", "sm_get_info",
     "sm_fill_web_holes", "sm_set_web", "sm_draw_contour_map", "sm_download", "sm_download_web_u8",
     "sm_run_batch", "sm_band_rows",
     "sm_multi_create", "sm_multi_run_batch", "sm_multi_device_count", "sm_multi_destroy",
@@ -63,6 +64,7 @@ def lib() -> C.CDLL:
         L.sm_set_stream.argtypes = [vp, vp]
         L.sm_set_kernel.argtypes = [vp, i]
         L.sm_set_option.argtypes = [vp, i, i]
+        L.sm_get_info.argtypes = [vp, i]
         L.sm_synchronize.argtypes = [vp]
         L.sm_upload_f64.argtypes = [vp, vp, vp]
         L.sm_upload_u8.argtypes = [vp, vp, vp]
@@ -173,6 +175,9 @@ class StereoContext:
 
     def set_option(self, option, value):
         _check(lib().sm_set_option(self._c, option, int(value)))
+
+    def get_info(self, what):
+        return _check(lib().sm_get_info(self._c, what))
 
     def set_stream(self, cuda_stream: int):
         _check(lib().sm_set_stream(self._c, C.c_void_p(cuda_stream)))

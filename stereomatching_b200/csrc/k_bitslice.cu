@@ -109,7 +109,7 @@ struct WS {
     static_assert(N * EC <= 512, "the vertical window must fit one TMEM allocation");
 };
 
-enum { MODE_LAUNCH = 0, MODE_PREPARE = 1 };
+enum { MODE_LAUNCH = 0, MODE_PREPARE = 1, MODE_TMEM_COLUMNS = 2 };
 
 // throughput mode (several pairs per launch): a warp's run of rows, in windows
 inline int throughput_run_windows()
@@ -740,6 +740,7 @@ template <int HALF, int NW, int SEG, bool C2>
 int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
 {
     using C = WS<HALF, NW, SEG>;
+    if (mode == MODE_TMEM_COLUMNS) return C::TCOLS;
     // MULTI: more than one chunk of 32*NW shifts, i.e. (best, web) are merged across passes
     // (one word per lane is only chosen for 32 shifts or fewer: no MULTI flavour of it is instantiated)
     const bool multi = !C2 && NW == 2 && h.g.D > 32 * NW;
@@ -749,14 +750,14 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
     }
     auto kern = C2 ? k_bitslice<HALF, NW, SEG, false, C2>
                    : (multi ? k_bitslice<HALF, NW, SEG, NW == 2, false> : k_bitslice<HALF, NW, SEG, false, false>);
-    // the resident warps per SM of this instantiation on the current device: asked once per context
-    // (prepare_bitslice at sm_create, kept in HotArgs::blocks_per_sm), never cached in a static
-    int warps_per_sm = h.blocks_per_sm;
-    if (mode == MODE_PREPARE || warps_per_sm <= 0) {
+    // resident warps per SM of this instantiation: what shared memory, the 512 TMEM columns and the register file
+    // allow, all known at compile time (WS::CTAS_PER_SM is also the kernel's __launch_bounds__).  (The occupancy
+    // API is not asked: it answers 1 CTA per SM for these kernels, whatever carve-out is set, while the
+    // hardware runs the 4 that ncu's launch__occupancy_limit_* report.)
+    const int warps_per_sm = C::CTAS_PER_SM * C::WPC;
+    if (mode == MODE_PREPARE) {
         SM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_REQ));
-        int occ = 0;
-        SM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * C::WPC, C::SMEM_REQ));
-        warps_per_sm = (occ > 0 ? occ : 1) * C::WPC;
+        SM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     if (mode == MODE_PREPARE) return warps_per_sm;  // module loaded, attribute set
     BitsliceArgs a;
@@ -783,19 +784,25 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
         segs = h.force_segs;  // development hook (sm_set_option)
     } else if (h.npairs == 1) {
         // latency mode (one pair per launch).  All CTAs do the same work: a run of R rows costs R + 2*half
-        // window-filling rows + a fixed start-up, and the launch takes as many rounds of that as its CTAs need
-        // waves of the machine.  Pick the number of runs that minimises rounds x cost (short runs pay more
-        // filling rows, long runs leave slots empty); a cost model instead of timing candidates at sm_create.
+        // window-filling rows + a fixed start-up.  The kernel is bound by the ALU pipe, so an SM takes as long as
+        // the work of the CTAs that land on it (they are dealt round-robin: ceil(CTAs / SMs) on the fullest),
+        // stretched when too few warps are resident to keep the pipe busy (measured: about 55 % of the pipe
+        // with 4 warps per SM, 93 % with 8, flat from 12).  Pick the number of runs that minimises that
+        // (short runs pay more filling rows, long runs leave SMs idle or thin); a cost model instead of
+        // timing candidates at sm_create.
         const int start_rows = 4;
-        long best_cost = -1;
+        double best_cost = -1.0;
         segs = 1;
         for (int sg = 1; sg <= max_segs; sg++) {
             int rows, got = shape(sg, rows);
             if (got != sg) continue;
-            const long waves = ((long)ctas_per_run * got + slots - 1) / slots;
-            const long cost = waves * (rows + 2 * HALF + start_rows);
+            const int ctas = ctas_per_run * got;
+            const int per_sm = (ctas + num_sms - 1) / num_sms;
+            const int resident = (per_sm < C::CTAS_PER_SM ? per_sm : C::CTAS_PER_SM) * C::WPC;
+            const double eff = resident >= 12 ? 1.0 : (resident <= 4 ? 0.55 : 0.55 + 0.45 * (resident - 4) / 8.0);
+            const double cost = per_sm * (double)(rows + 2 * HALF + start_rows) / eff;
             if (best_cost < 0 || cost < best_cost) best_cost = cost, segs = got;
-            if (waves > 4) break;
+            if (ctas > 6 * slots) break;
         }
     } else {
         // throughput mode (several pairs per launch): runs of about 32 windows -- the launch may be several waves
@@ -910,5 +917,7 @@ int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 // Loads the kernel this geometry will use and sets its shared-memory attribute, so that the first
 // sm_match_wta call pays none of that; returns its resident warps per SM (for HotArgs::blocks_per_sm).
 int prepare_bitslice(const HotArgs &h, int num_sms) { return dispatch(h, num_sms, nullptr, MODE_PREPARE); }
+
+int bitslice_tmem_columns(const HotArgs &h) { return dispatch(h, 0, nullptr, MODE_TMEM_COLUMNS); }
 
 }  // namespace smb

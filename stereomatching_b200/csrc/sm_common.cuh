@@ -93,6 +93,7 @@ int launch_direct(const HotArgs &a, cudaStream_t s);
 int launch_bitslice(const HotArgs &a, int num_sms, cudaStream_t s);
 bool bitslice_supports(int half, int D);
 int prepare_bitslice(const HotArgs &a, int num_sms);
+int bitslice_tmem_columns(const HotArgs &a);
 int bitslice_pairs_per_launch(const HotArgs &a, int num_sms, int max_pairs);
 // force the (lazily loaded) kernels of each translation unit into the context
 void warm_edges(int variant);

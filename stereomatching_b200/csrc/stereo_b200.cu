@@ -7,6 +7,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -487,6 +490,17 @@ extern "C" int sm_set_option(sm_ctx *c, int option, int value)
         c->tuned_segs = value;
         return SM_OK;
     default: set_error("sm_set_option: unknown option %d", option); return SM_ERR_ARG;
+    }
+}
+
+extern "C" int sm_get_info(sm_ctx *c, int what)
+{
+    SM_ENTER(c);
+    switch (what) {
+    case SM_INFO_WARPS_PER_SM: return c->occ;
+    case SM_INFO_PAIRS_PER_LAUNCH: return c->batch_group_cap;
+    case SM_INFO_TMEM_COLUMNS: return bitslice_supports(c->half, c->D) ? bitslice_tmem_columns(hot_args(c, c->best, c->web)) : 0;
+    default: set_error("sm_get_info: unknown item %d", what); return SM_ERR_ARG;
     }
 }
 
@@ -1059,9 +1073,86 @@ extern "C" int sm_run_batch(sm_ctx *c, int n_pairs, const uint8_t *first, const 
 // takes a contiguous range of the batch (the caller's arrays are contiguous, so every stage of its
 // sm_run_batch pipeline stays a single copy).  No cross-device traffic, no collective.
 
+// One persistent host thread per device slot (sm_multi_*, sm_bands_*): created with the object, parked on a
+// condition variable between calls, joined at destroy -- no thread is created or joined inside a run call.
+namespace {
+
+class SlotWorkers {
+public:
+    explicit SlotWorkers(int n) : jobs_((size_t)n), state_((size_t)n, 0)
+    {
+        for (int k = 0; k < n; k++) {
+            try {
+                threads_.emplace_back([this, k] { loop(k); });
+            } catch (...) {  // no thread to be had: that slot's work runs on the calling thread
+                break;
+            }
+        }
+    }
+    ~SlotWorkers()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    // run job(k) for every slot k and wait for all of them
+    void run_all(const std::function<void(int)> &job)
+    {
+        const int n = (int)jobs_.size(), nt = (int)threads_.size();
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int k = 0; k < nt; k++) {
+                jobs_[(size_t)k] = job;
+                state_[(size_t)k] = 1;
+            }
+        }
+        cv_.notify_all();
+        for (int k = nt; k < n; k++) job(k);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] {
+            for (int k = 0; k < nt; k++)
+                if (state_[(size_t)k] != 0) return false;
+            return true;
+        });
+    }
+
+private:
+    void loop(int k)
+    {
+        for (;;) {
+            std::function<void(int)> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return quit_ || state_[(size_t)k] == 1; });
+                if (quit_) return;
+                job = jobs_[(size_t)k];
+                state_[(size_t)k] = 2;
+            }
+            job(k);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                state_[(size_t)k] = 0;
+            }
+            done_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::function<void(int)>> jobs_;
+    std::vector<int> state_;  // 0 idle, 1 job posted, 2 running
+    std::vector<std::thread> threads_;
+    bool quit_ = false;
+};
+
+}  // namespace
+
 struct sm_multi {
     int n = 0;
     sm_ctx **ctx = nullptr;
+    SlotWorkers *workers = nullptr;
 };
 
 extern "C" int sm_multi_create(sm_multi **out, const int *devices, int n_devices, int width, int height,
@@ -1090,6 +1181,7 @@ extern "C" int sm_multi_create(sm_multi **out, const int *devices, int n_devices
             return rc;
         }
     }
+    m->workers = new (std::nothrow) SlotWorkers(n_devices);
     *out = m;
     return SM_OK;
 }
@@ -1097,6 +1189,7 @@ extern "C" int sm_multi_create(sm_multi **out, const int *devices, int n_devices
 extern "C" int sm_multi_destroy(sm_multi *m)
 {
     if (!m) return SM_OK;
+    delete m->workers;
     for (int d = 0; d < m->n; d++) sm_destroy(m->ctx[d]);
     free(m->ctx);
     delete m;
@@ -1112,25 +1205,20 @@ extern "C" int sm_multi_run_batch(sm_multi *m, int n_pairs, const uint8_t *first
     const int N = m->n;
     std::vector<int> rcs((size_t)N, SM_OK);
     std::vector<std::string> errs((size_t)N);
-    std::vector<std::thread> threads;
     const size_t n = m->ctx[0]->npix();
-    for (int d = 0; d < N; d++) {
+    auto work = [&](int d) {
         const int k0 = (int)((long long)n_pairs * d / N), k1 = (int)((long long)n_pairs * (d + 1) / N);
-        auto work = [=, &rcs, &errs]() {
-            if (k1 <= k0) return;
-            uint8_t *w8 = (uint8_t *)web_out;
-            void *wout = web_u8 ? (void *)(w8 + (size_t)k0 * n) : (void *)((int32_t *)web_out + (size_t)k0 * n);
-            rcs[d] = sm_run_batch(m->ctx[d], k1 - k0, first + (size_t)k0 * n, second + (size_t)k0 * n, threshold, wout,
-                                  web_u8, best_out ? best_out + (size_t)k0 * n : nullptr);
-            if (rcs[d]) errs[d] = sm_last_error();  // the message is per thread: carry it to the caller's
-        };
-        try {
-            threads.emplace_back(work);
-        } catch (...) {  // no thread to be had: this slot's shard runs on the calling thread
-            work();
-        }
-    }
-    for (auto &t : threads) t.join();
+        if (k1 <= k0) return;
+        uint8_t *w8 = (uint8_t *)web_out;
+        void *wout = web_u8 ? (void *)(w8 + (size_t)k0 * n) : (void *)((int32_t *)web_out + (size_t)k0 * n);
+        rcs[(size_t)d] = sm_run_batch(m->ctx[d], k1 - k0, first + (size_t)k0 * n, second + (size_t)k0 * n, threshold, wout,
+                                      web_u8, best_out ? best_out + (size_t)k0 * n : nullptr);
+        if (rcs[(size_t)d]) errs[(size_t)d] = sm_last_error();  // the message is per thread: carry it to the caller's
+    };
+    if (m->workers)
+        m->workers->run_all(work);
+    else
+        for (int d = 0; d < N; d++) work(d);
     for (int d = 0; d < N; d++)
         if (rcs[d]) {
             set_error("sm_multi_run_batch: device slot %d: %s", d, errs[d].c_str());
@@ -1149,11 +1237,13 @@ extern "C" int sm_multi_run_batch(sm_multi *m, int n_pairs, const uint8_t *first
 struct sm_bands {
     int n = 0;
     sm_ctx **ctx = nullptr;
+    SlotWorkers *workers = nullptr;
 };
 
 extern "C" int sm_bands_destroy(sm_bands *b)
 {
     if (!b) return SM_OK;
+    delete b->workers;
     for (int d = 0; d < b->n; d++) sm_destroy(b->ctx[d]);
     free(b->ctx);
     delete b;
@@ -1187,6 +1277,7 @@ extern "C" int sm_bands_create(sm_bands **out, const int *devices, int n_devices
             return rc;
         }
     }
+    b->workers = new (std::nothrow) SlotWorkers(n_devices);
     *out = b;
     return SM_OK;
 }
@@ -1198,25 +1289,20 @@ extern "C" int sm_bands_run(sm_bands *b, const uint8_t *first, const uint8_t *se
     const int N = b->n;
     std::vector<int> rcs((size_t)N, SM_OK);
     std::vector<std::string> errs((size_t)N);
-    std::vector<std::thread> threads;
-    for (int d = 0; d < N; d++) {
-        auto work = [=, &rcs, &errs]() {
-            sm_ctx *c = b->ctx[d];
-            int rc = sm_upload_u8(c, first, second);  // a band context copies only the rows it needs
-            if (!rc) rc = sm_edges(c, threshold);
-            if (!rc) rc = sm_match_wta(c);
-            if (!rc) rc = sm_download(c, SM_WEB, 0, web_out);  // ... and writes only its own rows
-            if (!rc && best_out) rc = sm_download(c, SM_BEST, 0, best_out);
-            rcs[d] = rc;
-            if (rc) errs[d] = sm_last_error();
-        };
-        try {
-            threads.emplace_back(work);
-        } catch (...) {
-            work();
-        }
-    }
-    for (auto &t : threads) t.join();
+    auto work = [&](int d) {
+        sm_ctx *c = b->ctx[d];
+        int rc = sm_upload_u8(c, first, second);  // a band context copies only the rows it needs
+        if (!rc) rc = sm_edges(c, threshold);
+        if (!rc) rc = sm_match_wta(c);
+        if (!rc) rc = sm_download(c, SM_WEB, 0, web_out);  // ... and writes only its own rows
+        if (!rc && best_out) rc = sm_download(c, SM_BEST, 0, best_out);
+        rcs[(size_t)d] = rc;
+        if (rc) errs[(size_t)d] = sm_last_error();
+    };
+    if (b->workers)
+        b->workers->run_all(work);
+    else
+        for (int d = 0; d < N; d++) work(d);
     for (int d = 0; d < N; d++)
         if (rcs[d]) {
             set_error("sm_bands_run: band %d: %s", d, errs[d].c_str());
