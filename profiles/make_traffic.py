@@ -3,7 +3,7 @@
 (k_bitslice, several pairs per launch) into profiles/traffic.json, which bench.py reads for roofline.traffic,
 roofline.issue and roofline.alu_mix (executed instruction counts cannot be measured outside a profiler).
 
-    python profiles/make_traffic.py gpurun_out/<report>.ncu-rep <pairs in the captured launch> > profiles/traffic.json
+    python profiles/make_traffic.py gpurun_out/<report>.ncu-rep [pairs in the captured launch] > profiles/traffic.json
 """
 import collections
 import csv
@@ -18,13 +18,17 @@ LSU = {"LDS", "STS", "LDG", "STG", "LD", "ST", "LDTM", "STTM", "SHFL"}
 
 
 def main():
-    path, pairs = sys.argv[1], int(sys.argv[2])
+    path = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, data = rows[0], rows[2:]
     r = data[0]
     g = lambda m: float(r[h.index(m)].replace(",", "")) if m in h else None  # noqa: E731
     units = rows[1]
+    # pairs in the captured launch = the grid's z dimension (one pair per z-slice, k_bitslice.cu); an explicit
+    # second argument overrides it
+    gz = r[h.index("Grid Size")] if "Grid Size" in h else ""
+    pairs = int(sys.argv[2]) if len(sys.argv) > 2 else int(gz.strip("() ").split(",")[-1])
     scale = lambda m: {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(units[h.index(m)], 1.0)  # noqa: E731
     src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"],
                          capture_output=True, text=True).stdout
