@@ -273,6 +273,13 @@ class Env:
             return float(t.item())
         return x
 
+    def rsum(self, x):
+        if self.world > 1:
+            t = self.torch.tensor([x], dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            return float(t.item())
+        return x
+
     def all_true(self, ok):
         return self.rmax(0.0 if ok else 1.0) == 0.0
 
@@ -380,11 +387,13 @@ def leg_config3_bands(env, smb, variant_name):
     with smb.StereoContext(w, h, d, sw, variant, device=env.local_rank, rows=(r0, r1)) as c:
         stream = torch.cuda.Stream(device=env.dev)
         c.set_stream(stream.cuda_stream)
-        c.upload_u8(pin_l.array, pin_r.array)
-        c.edges(THRESHOLD)
-        # resident: the band's edge maps are on the device; a step = pack + match/box/WTA of the band
-        e1 = torch.from_numpy(c.download(smb.EDGES1)).to(env.dev)
-        e2 = torch.from_numpy(c.download(smb.EDGES2)).to(env.dev)
+        # resident: whole-frame edge maps on the device (a band context downloads only its own rows, and the
+        # band's pack kernel needs the halo rows as well); a step = pack + match/box/WTA of the band
+        with smb.StereoContext(w, h, d, sw, variant, device=env.local_rank) as cf:
+            cf.upload_u8(pin_l.array, pin_r.array)
+            cf.edges(THRESHOLD)
+            e1 = torch.from_numpy(cf.download(smb.EDGES1)).to(env.dev)
+            e2 = torch.from_numpy(cf.download(smb.EDGES2)).to(env.dev)
         best = torch.empty((h, w), dtype=torch.int32, device=env.dev)
         web = torch.empty_like(best)
         run = lambda: c.match_wta_dev(e1.data_ptr(), e2.data_ptr(), best.data_ptr(), web.data_ptr())  # noqa: E731
@@ -410,9 +419,11 @@ def leg_config3_bands(env, smb, variant_name):
         # parity: this rank's rows against the reference's golden CRCs of the 16 row bands of the whole frame
         nb = len(g["web_bands16"])
         mine = [b for b in range(nb) if r0 <= h * b // nb and h * (b + 1) // nb <= r1]
-        ok = len(mine) > 0 and all(_crc(pin_web.array[h * b // nb:h * (b + 1) // nb]) == g["web_bands16"][b] for b in mine)
-        ok = ok and all(_crc(web[h * b // nb:h * (b + 1) // nb].cpu().numpy()) == g["web_bands16"][b] for b in mine)
-    out["parity"] = {"bands_equal_reference_golden": env.all_true(ok),
+        ok_e2e = len(mine) > 0 and all(_crc(pin_web.array[h * b // nb:h * (b + 1) // nb]) == g["web_bands16"][b] for b in mine)
+        ok_res = len(mine) > 0 and all(_crc(web[h * b // nb:h * (b + 1) // nb].cpu().numpy()) == g["web_bands16"][b] for b in mine)
+        ok = ok_e2e and ok_res
+    out["parity"] = {"bands_equal_reference_golden": env.all_true(ok), "resident": env.all_true(ok_res),
+                     "e2e": env.all_true(ok_e2e),
                      "checked": "each rank's rows of web (resident and e2e) vs the per-band CRC32s of the reference's "
                                 "whole-frame output (tests/golden synth/c3)"}
     pin_l.free(), pin_r.free(), pin_web.free()
@@ -568,7 +579,14 @@ def run_b200_arm(a, rank, world, local_rank):
     parity["e2e_webs_checked"] = check_webs(lambda k: hweb8.array[k].astype(np.int32), Be, "e2e (u8 web)")
     parity["e2e_i32_webs_checked"] = check_webs(lambda k: hweb.array[k], Be, "e2e (i32 web)")
     # the link's own ceiling for those two calls: pinned host<->device copies, both directions at once
-    h2d_gbs, d2h_gbs = benchlib.measure_copy_peak(local_rank, 2)
+    # -- every rank measures its own link while all the others do the same (they share the host's fabric), and the
+    # job's ceiling is the sum of the per-rank ceilings
+    # under the traffic mix of the call: 2 bytes up per byte down (u8 web), 2 up per 4 down (i32 web)
+    h2d_gbs, d2h_gbs, mixes = benchlib.measure_copy_concurrent(local_rank, env.barrier, mixes=((2, 1), (2, 4)))
+    (sec8, up8, _), (sec32, up32, _) = mixes
+    ceil8 = env.rsum(up8 / (2.0 * W * H) / sec8 * W * H * D / 1e6)      # pairs per round / seconds per round
+    ceil32 = env.rsum(up32 / (2.0 * W * H) / sec32 * W * H * D / 1e6)
+    h2d_all, d2h_all = env.rsum(h2d_gbs), env.rsum(d2h_gbs)
 
     # ---- the other sharded configs north_star names, same process, after the headline legs ---------------------
     c4 = leg_config4_pairs(env, smb, a.variant) if not a.no_extra else None
@@ -632,8 +650,6 @@ def run_b200_arm(a, rank, world, local_rank):
         }
         cpu = cpu_baseline_single_core() if world == 1 and not a.no_cpu else None
         refcuda = whole_algorithm_baselines(pairs[0], a.variant) if world == 1 and not a.no_cpu else None
-        ceil8 = world * W * H * D / max(2 * W * H / (h2d_gbs * 1e9), W * H / (d2h_gbs * 1e9)) / 1e6
-        ceil32 = world * W * H * D / max(2 * W * H / (h2d_gbs * 1e9), 4 * W * H / (d2h_gbs * 1e9)) / 1e6
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "MDE/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
@@ -654,8 +670,13 @@ def run_b200_arm(a, rank, world, local_rank):
                            "(values 1..64; the compact result format of the ABI for num_shifts <= 255)",
                     "timer": "host wall clock around synchronised API calls, max over ranks",
                     "frames_per_s": e2e8_val * 1e6 / (W * H * D), "gpu_launches_per_step": e2e_launches,
-                    "link": {"h2d_GBps": h2d_gbs, "d2h_GBps": d2h_gbs,
-                             "how": "benchlib: 256 MB pinned copies, both directions at once, best of 3 (rank 0)",
+                    "link": {"h2d_GBps": h2d_gbs, "d2h_GBps": d2h_gbs, "h2d_GBps_all_ranks": h2d_all,
+                             "d2h_GBps_all_ranks": d2h_all,
+                             "how": "benchlib: pinned copies of up to 256 MB on two free-running streams, mean of 6 "
+                                    "rounds, every rank measuring its own link at the same time (after a barrier). "
+                                    "h2d_GBps/d2h_GBps: both directions saturated (rank 0's; *_all_ranks: summed). "
+                                    "The ceilings time the call's own traffic mix (2 bytes up per byte down for the "
+                                    "u8 web, 2 up per 4 down for the i32 web) and sum the per-rank pair rates",
                              "ceiling_MDE_per_s": ceil8, "frac_of_ceiling": e2e8_val / ceil8,
                              "note": "per pair 2 u8 images go up and one u8 web comes down; the slower direction "
                                      "bounds pairs/s, compute overlaps"},

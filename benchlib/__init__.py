@@ -19,6 +19,9 @@ def _peaks():
         _lib = C.CDLL(path)
         _lib.smb_measure_int_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lib.smb_measure_copy_peak.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
+        _lib.smb_copy_peak_setup.argtypes = [C.c_int]
+        _lib.smb_copy_peak_measure.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        _lib.smb_copy_peak_mix.argtypes = [C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     return _lib
 
 
@@ -36,3 +39,29 @@ def measure_copy_peak(device: int = 0, mode: int = 2):
     if _peaks().smb_measure_copy_peak(device, mode, g) != 0:
         raise RuntimeError("smb_measure_copy_peak failed")
     return g[0], g[1]
+
+
+def measure_copy_concurrent(device: int, barrier, mixes=(), reps: int = 6):
+    """This rank's link while every other rank measures its own at the same time: buffers are set up first,
+    `barrier()` lines the ranks up, then 256 MB copies are timed (mean rate, not the best repetition: contention
+    is the point).  Returns (H2D GB/s, D2H GB/s) with both directions saturated, and for every (up, down) byte
+    ratio in `mixes` the seconds one round of that mix takes (up + down = at most 256 MB each)."""
+    L = _peaks()
+    if L.smb_copy_peak_setup(device) != 0:
+        raise RuntimeError("smb_copy_peak_setup failed")
+    try:
+        barrier()
+        g = (C.c_double * 2)()
+        if L.smb_copy_peak_measure(2, reps, 0, g) != 0:
+            raise RuntimeError("smb_copy_peak_measure failed")
+        out = []
+        for up, down in mixes:
+            barrier()
+            unit = (256 << 20) // max(up, down)
+            sec = C.c_double()
+            if L.smb_copy_peak_mix(up * unit, down * unit, reps, C.byref(sec)) != 0:
+                raise RuntimeError("smb_copy_peak_mix failed")
+            out.append((sec.value, up * unit, down * unit))
+        return g[0], g[1], out
+    finally:
+        L.smb_copy_peak_teardown()

@@ -105,51 +105,114 @@ extern "C" int smb_measure_int_peak(int device, int mode, double *gops_per_s)
 // Host <-> device copy bandwidth of this GPU's link from pinned memory: the ceiling of the
 // end-to-end (host buffers) figure.  mode 0: H2D alone, 1: D2H alone, 2: both directions at
 // once (two streams), reported per direction (H2D in gbs[0], D2H in gbs[1]).
+// Three calls so that several ranks can measure AT THE SAME TIME (set up, barrier in the caller, measure):
+// with eight GPUs on one host the per-GPU figure under contention is what bounds the end-to-end run.
+namespace {
+struct CopyPeak {
+    int device = -1, prev = -1;
+    void *h[2] = {nullptr, nullptr}, *d[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t e0[2] = {nullptr, nullptr}, e1[2] = {nullptr, nullptr};
+} g_cp;
+const size_t kCopyBytes = (size_t)256 << 20;
+}  // namespace
+
+extern "C" int smb_copy_peak_setup(int device)
+{
+    if (g_cp.device >= 0) return -1;
+    cudaGetDevice(&g_cp.prev);
+    PK_CUDA(cudaSetDevice(device));
+    for (int k = 0; k < 2; k++) {
+        PK_CUDA(cudaHostAlloc(&g_cp.h[k], kCopyBytes, cudaHostAllocDefault));
+        memset(g_cp.h[k], k + 1, kCopyBytes);
+        PK_CUDA(cudaMalloc(&g_cp.d[k], kCopyBytes));
+        PK_CUDA(cudaStreamCreateWithFlags(&g_cp.st[k], cudaStreamNonBlocking));
+        PK_CUDA(cudaEventCreate(&g_cp.e0[k]));
+        PK_CUDA(cudaEventCreate(&g_cp.e1[k]));
+    }
+    g_cp.device = device;
+    return 0;
+}
+
+// reps timed repetitions after one warm-up; best != 0: the fastest repetition, else the mean rate over all of them
+extern "C" int smb_copy_peak_measure(int mode, int reps, int best, double *gbs)
+{
+    if (!gbs || mode < 0 || mode > 2 || reps < 1 || g_cp.device < 0) return -1;
+    gbs[0] = gbs[1] = 0.0;
+    double total_ms[2] = {0.0, 0.0};
+    for (int rep = 0; rep <= reps; rep++) {  // rep 0 is the warm-up
+        for (int k = 0; k < 2; k++) {
+            if (mode != 2 && k != mode) continue;
+            PK_CUDA(cudaEventRecord(g_cp.e0[k], g_cp.st[k]));
+            if (k == 0)
+                PK_CUDA(cudaMemcpyAsync(g_cp.d[0], g_cp.h[0], kCopyBytes, cudaMemcpyHostToDevice, g_cp.st[0]));
+            else
+                PK_CUDA(cudaMemcpyAsync(g_cp.h[1], g_cp.d[1], kCopyBytes, cudaMemcpyDeviceToHost, g_cp.st[1]));
+            PK_CUDA(cudaEventRecord(g_cp.e1[k], g_cp.st[k]));
+        }
+        for (int k = 0; k < 2; k++) {
+            if (mode != 2 && k != mode) continue;
+            PK_CUDA(cudaEventSynchronize(g_cp.e1[k]));
+            float ms = 0;
+            PK_CUDA(cudaEventElapsedTime(&ms, g_cp.e0[k], g_cp.e1[k]));
+            if (rep == 0) continue;
+            total_ms[k] += ms;
+            const double g = (double)kCopyBytes / (ms * 1e-3) / 1e9;
+            if (best && g > gbs[k]) gbs[k] = g;
+        }
+    }
+    if (!best)
+        for (int k = 0; k < 2; k++)
+            if (total_ms[k] > 0) gbs[k] = (double)kCopyBytes * reps / (total_ms[k] * 1e-3) / 1e9;
+    return 0;
+}
+
+// The link under the traffic MIX of a call: `reps` rounds of h2d_bytes up and d2h_bytes down (each at most 256 MB),
+// the two directions on their own streams and free-running; seconds per round by the host clock.
+extern "C" int smb_copy_peak_mix(size_t h2d_bytes, size_t d2h_bytes, int reps, double *seconds)
+{
+    if (!seconds || reps < 1 || g_cp.device < 0 || h2d_bytes > kCopyBytes || d2h_bytes > kCopyBytes) return -1;
+    for (int rep = -1; rep < reps; rep++) {  // rep -1 is the warm-up
+        if (rep == 0) {
+            PK_CUDA(cudaStreamSynchronize(g_cp.st[0]));
+            PK_CUDA(cudaStreamSynchronize(g_cp.st[1]));
+            PK_CUDA(cudaEventRecord(g_cp.e0[0], g_cp.st[0]));
+            PK_CUDA(cudaEventRecord(g_cp.e0[1], g_cp.st[1]));
+        }
+        if (h2d_bytes) PK_CUDA(cudaMemcpyAsync(g_cp.d[0], g_cp.h[0], h2d_bytes, cudaMemcpyHostToDevice, g_cp.st[0]));
+        if (d2h_bytes) PK_CUDA(cudaMemcpyAsync(g_cp.h[1], g_cp.d[1], d2h_bytes, cudaMemcpyDeviceToHost, g_cp.st[1]));
+    }
+    PK_CUDA(cudaEventRecord(g_cp.e1[0], g_cp.st[0]));
+    PK_CUDA(cudaEventRecord(g_cp.e1[1], g_cp.st[1]));
+    float ms0 = 0, ms1 = 0;
+    PK_CUDA(cudaEventSynchronize(g_cp.e1[0]));
+    PK_CUDA(cudaEventSynchronize(g_cp.e1[1]));
+    PK_CUDA(cudaEventElapsedTime(&ms0, g_cp.e0[0], g_cp.e1[0]));
+    PK_CUDA(cudaEventElapsedTime(&ms1, g_cp.e0[1], g_cp.e1[1]));
+    *seconds = (double)(ms0 > ms1 ? ms0 : ms1) * 1e-3 / reps;
+    return 0;
+}
+
+extern "C" int smb_copy_peak_teardown(void)
+{
+    if (g_cp.device < 0) return 0;
+    for (int k = 0; k < 2; k++) {
+        cudaEventDestroy(g_cp.e0[k]);
+        cudaEventDestroy(g_cp.e1[k]);
+        cudaStreamDestroy(g_cp.st[k]);
+        cudaFree(g_cp.d[k]);
+        cudaFreeHost(g_cp.h[k]);
+    }
+    if (g_cp.prev >= 0) cudaSetDevice(g_cp.prev);
+    g_cp = CopyPeak();
+    return 0;
+}
+
 extern "C" int smb_measure_copy_peak(int device, int mode, double *gbs)
 {
     if (!gbs || mode < 0 || mode > 2) return -1;
-    int prev = -1;
-    cudaGetDevice(&prev);
-    PK_CUDA(cudaSetDevice(device));
-    const size_t bytes = (size_t)256 << 20;
-    void *h[2] = {nullptr, nullptr}, *d[2] = {nullptr, nullptr};
-    cudaStream_t st[2];
-    cudaEvent_t e0[2], e1[2];
-    for (int k = 0; k < 2; k++) {
-        PK_CUDA(cudaHostAlloc(&h[k], bytes, cudaHostAllocDefault));
-        memset(h[k], k + 1, bytes);
-        PK_CUDA(cudaMalloc(&d[k], bytes));
-        PK_CUDA(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking));
-        PK_CUDA(cudaEventCreate(&e0[k]));
-        PK_CUDA(cudaEventCreate(&e1[k]));
-    }
-    gbs[0] = gbs[1] = 0.0;
-    for (int rep = 0; rep < 4; rep++) {  // rep 0 is the warm-up
-        for (int k = 0; k < 2; k++) {
-            if (mode != 2 && k != mode) continue;
-            PK_CUDA(cudaEventRecord(e0[k], st[k]));
-            if (k == 0)
-                PK_CUDA(cudaMemcpyAsync(d[0], h[0], bytes, cudaMemcpyHostToDevice, st[0]));
-            else
-                PK_CUDA(cudaMemcpyAsync(h[1], d[1], bytes, cudaMemcpyDeviceToHost, st[1]));
-            PK_CUDA(cudaEventRecord(e1[k], st[k]));
-        }
-        for (int k = 0; k < 2; k++) {
-            if (mode != 2 && k != mode) continue;
-            PK_CUDA(cudaEventSynchronize(e1[k]));
-            float ms = 0;
-            PK_CUDA(cudaEventElapsedTime(&ms, e0[k], e1[k]));
-            const double g = (double)bytes / (ms * 1e-3) / 1e9;
-            if (rep > 0 && g > gbs[k]) gbs[k] = g;
-        }
-    }
-    for (int k = 0; k < 2; k++) {
-        cudaEventDestroy(e0[k]);
-        cudaEventDestroy(e1[k]);
-        cudaStreamDestroy(st[k]);
-        cudaFree(d[k]);
-        cudaFreeHost(h[k]);
-    }
-    if (prev >= 0) cudaSetDevice(prev);
-    return 0;
+    if (smb_copy_peak_setup(device)) return -1;
+    int rc = smb_copy_peak_measure(mode, 3, 1, gbs);
+    smb_copy_peak_teardown();
+    return rc;
 }

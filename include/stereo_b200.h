@@ -87,7 +87,10 @@ typedef enum sm_option {
 typedef enum sm_info {
     SM_INFO_WARPS_PER_SM = 1,     /* resident warps per SM of the kernel instantiation this geometry uses */
     SM_INFO_PAIRS_PER_LAUNCH = 2, /* pairs the batch entries put into one launch (0 before the first batch call) */
-    SM_INFO_TMEM_COLUMNS = 3      /* tensor-memory columns one CTA allocates for the vertical-window ring */
+    SM_INFO_TMEM_COLUMNS = 3,     /* tensor-memory columns one CTA allocates for the vertical-window ring */
+    SM_INFO_EDGE_THRESHOLDS = 4   /* 1: the edge detector's current decision table is exactly a threshold table
+                                     (symmetric and monotone, checked bit by bit on the device) and the fast
+                                     detector uses it; 0: it falls back to the bit table; -1: no table built yet */
 } sm_info;
 
 /* ---- library-level -------------------------------------------------------- */

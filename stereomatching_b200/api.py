@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("STEREO_B200_LIB") or os.path.join(HERE, "libstereo_b2
 WRAP, GHOST = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_BITSLICE = 0, 1, 2
 OPT_EDGES_FP64, OPT_PIPE_GROUP, OPT_ROW_RUNS = 1, 2, 3
-INFO_WARPS_PER_SM, INFO_PAIRS_PER_LAUNCH, INFO_TMEM_COLUMNS = 1, 2, 3
+INFO_WARPS_PER_SM, INFO_PAIRS_PER_LAUNCH, INFO_TMEM_COLUMNS, INFO_EDGE_THRESHOLDS = 1, 2, 3, 4
 (EDGES1, EDGES2, MATCH, SCORE_ALL, SCORE, BEST, WEB, WEB_FILLED, OUTPUT) = range(9)
 _PLANE_DTYPE = {EDGES1: np.uint8, EDGES2: np.uint8, MATCH: np.uint8, SCORE_ALL: np.int32,
                 SCORE: np.int32, BEST: np.int32, WEB: np.int32, WEB_FILLED: np.int32,

@@ -319,7 +319,7 @@ __device__ __forceinline__ void csa_planes(const uint32_t (&a)[N], uint32_t (&P)
 // WRAP mode and away from the borders in GHOST mode), so the validity select drops out.
 // The first 2*HALF match words only fill the window: they are summed by a carry-save tree
 // instead of 2*HALF counter steps; from then on one word enters and one leaves per step.
-template <int HALF, int NW, int SEG, bool VALID_ALL>
+template <int HALF, int NW, int SEG, bool VALID_ALL, bool HP>
 __device__ __forceinline__ void walk(const uint32_t (&q)[3], const uint32_t (&lw)[2], const uint32_t (&vw)[2],
                                      uint4 *hq, uint32_t *h5, uint32_t *mq)
 {
@@ -327,11 +327,23 @@ __device__ __forceinline__ void walk(const uint32_t (&q)[3], const uint32_t (&lw
     constexpr int N = C::N, KH = C::KH, STEPS = C::STEPS;
     uint32_t P[5] = {0, 0, 0, 0, 0};
     uint32_t m[STEPS];
+    const uint32_t nl[2] = {~lw[0], ~lw[1]};
+    // HP: flags of pixels u (bit t of a 64-bit window) and u + 16 (bit t + 16) land on bits 0 and 16 of one
+    // word; times 0xFFFF they are the two half-word masks (the multiply runs on the FMA pipe)
+    auto halves = [&](const uint32_t (&x)[2], int t) {
+        const uint32_t f = (t < 32 ? __funnelshift_r(x[0], x[1], t) : (x[1] >> (t - 32))) & 0x00010001u;
+        return f * 0xFFFFu;
+    };
     auto match_word = [&](int t) {
         const int qi = t >> 5;
         uint32_t mm = __funnelshift_r(q[qi], q[qi + 1 > 2 ? 2 : qi + 1], t & 31);
-        if (!(lw[t >> 5] & (1u << (t & 31)))) mm = ~mm;               // L(u) ? R : ~R
-        if (!VALID_ALL && !(vw[t >> 5] & (1u << (t & 31)))) mm = 0u;  // taps outside the image count nothing
+        if constexpr (HP) {
+            mm ^= halves(nl, t);                      // per half: L(u) ? R : ~R
+            if (!VALID_ALL) mm &= halves(vw, t);      // per half: taps outside the image count nothing
+        } else {
+            if (!(lw[t >> 5] & (1u << (t & 31)))) mm = ~mm;               // L(u) ? R : ~R
+            if (!VALID_ALL && !(vw[t >> 5] & (1u << (t & 31)))) mm = 0u;  // taps outside the image count nothing
+        }
         if (t >= HALF && t < HALF + SEG) mq[(t - HALF) * NW] = mm;    // centre word of pixel ws*SEG + t - HALF
         return mm;
     };
@@ -419,7 +431,13 @@ __device__ __forceinline__ void store_if(int32_t *p, int v, bool on)
 // two-word machinery unchanged; only the column of word w, the shift base and the winner-take-all (one per word)
 // differ.  It runs 32-shift problems at the per-word cost of the two-word kernel (8-row blocks, 17-row rings at
 // window 9) instead of the one-word kernel's 16-row blocks.
-template <int HALF, int NW, int SEG, bool MULTI, bool C2>
+//
+// HP ("half-word pairs", for num_shifts <= 16): a 32-bit match word of pixel u is R[u .. u+31], so its upper half IS
+// the 16-shift match word of pixel u + 16.  One word then serves TWO pixels, u and u + 16: walkers, counters, rings
+// and adders are unchanged (bit lanes never interact); only the complement / validity masks of a match word are
+// per half, the winner-take-all runs one chain per half, and lane l of a strip stands for the pixel columns
+// 32*(l/16) + l%16 and that + 16 (so a walker's 16-pixel segment covers 32 columns and a strip is twice as wide).
+template <int HALF, int NW, int SEG, bool MULTI, bool C2, bool HP>
 __global__ void __launch_bounds__(32 * WS<HALF, NW, SEG>::WPC, WS<HALF, NW, SEG>::CTAS_PER_SM)
 k_bitslice(BitsliceArgs a)
 {
@@ -461,10 +479,14 @@ k_bitslice(BitsliceArgs a)
     a.h.web += blockIdx.z * a.h.out_stride;
     const PackedGeom &g = a.h.g;
     static_assert(!C2 || (NW == 2 && !MULTI), "column pairs: two words, one 32-shift chunk");
-    const int x0 = (blockIdx.x * WPC + warp) * (C2 ? TW * NW : TW);
+    static_assert(!HP || (!MULTI && SEG == 16 && (C2 || NW == 1)), "half-word pairs: one chunk, 16-pixel segments");
+    constexpr int PW = HP ? 2 : 1;                    // pixels per word
+    constexpr int WCOLS = TW * PW;                    // pixel columns one word of all 32 lanes covers
+    constexpr int SCOLS = WCOLS * (C2 ? NW : 1);      // pixel columns per strip
+    const int x0 = (blockIdx.x * WPC + warp) * SCOLS;
     const int ja = blockIdx.y * a.rows_per_seg;
     const int jb = min(g.BH, ja + a.rows_per_seg);
-    const int ximg = x0 + lane;
+    const int ximg = HP ? x0 + 32 * (lane >> 4) + (lane & 15) : x0 + lane;
     const bool store_ok = ximg < g.W;
     const bool store_ok2 = ximg + TW < g.W;  // C2: the lane's second pixel
     const int nchunks = MULTI ? (g.D + 32 * NW - 1) / (32 * NW) : 1;
@@ -474,7 +496,7 @@ k_bitslice(BitsliceArgs a)
     // walker role of this lane
     const int ws = lane / (NW * RB), wl = lane - ws * (NW * RB);
     const int wr = wl / NW, ww = wl - wr * NW;
-    const int lbit = PADL + x0 + ws * SEG - HALF + (C2 ? TW * ww : 0);  // first pixel of the walk, as a bit of LA / LB
+    const int lbit = PADL + x0 + ws * SEG * PW - HALF + (C2 ? WCOLS * ww : 0);  // first pixel of the walk, as a bit of LA / LB
 
     auto load_h = [&](int slot, int w, uint32_t (&h)[5]) {
         const uint4 qv = Hq[(slot * NW + w) * HROW + lane];
@@ -511,6 +533,8 @@ k_bitslice(BitsliceArgs a)
             int lanes = g.D - 32 * (wg0 + (C2 ? 0 : w));
             valid[w] = lanes >= 32 ? 0xFFFFFFFFu : (lanes <= 0 ? 0u : ((1u << lanes) - 1u));
         }
+        // HP: the shift lanes of the lower and of the upper pixel of a word (num_shifts <= 16)
+        const uint32_t valid_lo = valid[0] & 0xFFFFu, valid_hi = valid_lo << 16;
         const int one = valid[0] ? 1 : g.W;  // always 1 (word 0 of a chunk has lanes); opaque to ptxas
         uint32_t V[NW][PV];
 #pragma unroll
@@ -560,11 +584,41 @@ k_bitslice(BitsliceArgs a)
             store_if(a.h.web + oidx + TW, idx1 + 1, store_ok2);
             oidx += g.W;
         };
+        // HP: the 2 * NW pixels of a lane of one finished row: word w covers columns ximg + w * WCOLS and that + 16
+        auto put_hp = [&](const int *bl, const int *il, const int *bh, const int *ih) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                const int xo = w * WCOLS;
+                store_if(a.h.best + oidx + xo, bl[w], ximg + xo < g.W);
+                store_if(a.h.web + oidx + xo, il[w] + 1, ximg + xo < g.W);
+                store_if(a.h.best + oidx + xo + 16, bh[w], ximg + xo + 16 < g.W);
+                store_if(a.h.web + oidx + xo + 16, ih[w] - 16 + 1, ximg + xo + 16 < g.W);
+            }
+            oidx += g.W;
+        };
         // winner-take-all of G rows held as Vs[G][NW][PV] / Ms[G][NW], then the stores: one WTA over both words
-        // of a pixel, or (C2) one per word, the 2*G single-word chains interleaved like rows
+        // of a pixel, or (C2) one per word, the 2*G single-word chains interleaved like rows, or (HP) one per
+        // half word: the lower halves of all words first, then the upper halves
         auto finish_rows = [&](auto gtag, const auto &Vs, const auto &Ms, const int *prev) {
             constexpr int G_ = decltype(gtag)::value;
-            if constexpr (!C2) {
+            if constexpr (HP) {
+                constexpr int NCH = G_ * NW;
+                uint32_t V1[NCH][1][PV], M1[NCH][1];
+#pragma unroll
+                for (int k = 0; k < G_; k++)
+#pragma unroll
+                    for (int w = 0; w < NW; w++) {
+                        M1[k * NW + w][0] = Ms[k][w];
+#pragma unroll
+                        for (int p = 0; p < PV; p++) V1[k * NW + w][0][p] = Vs[k][w][p];
+                    }
+                const uint32_t vl1[1] = {valid_lo}, vh1[1] = {valid_hi};
+                int bl[NCH], il[NCH], bh[NCH], ih[NCH];
+                wta<NCH, 1, PV>(V1, M1, vl1, one, bl, il);
+                wta<NCH, 1, PV>(V1, M1, vh1, one, bh, ih);
+#pragma unroll
+                for (int k = 0; k < G_; k++) put_hp(bl + k * NW, il + k * NW, bh + k * NW, ih + k * NW);
+            } else if constexpr (!C2) {
                 int best[G_], idx[G_];
                 wta<G_, NW, PV>(Vs, Ms, valid, one, best, idx);
 #pragma unroll
@@ -596,9 +650,15 @@ k_bitslice(BitsliceArgs a)
         // ring row of x = tslot + r, tslot < N, r < RB
         auto wrap_t = [&](int x) { return N >= RB ? wrap_hi(x, N) : x % N; };
 
-        for (int p0 = ja; p0 < last_pr; p0 += RB) {
-            const int nrows = min(RB, last_pr - p0);
+        // Blocks of RB padded rows.  The 2*HALF rows that only fill the window come first: a short block of
+        // (2*HALF) % RB rows, then whole blocks that add and never subtract or output (`filling`), so that every
+        // block from the first output row on is a whole, branch-free `steady` block (but the run's ragged end).
+        constexpr int FILL0 = (2 * HALF) % RB;
+        int nrows = 0;
+        for (int p0 = ja; p0 < last_pr; p0 += nrows) {
+            nrows = min((FILL0 != 0 && p0 == ja) ? FILL0 : RB, last_pr - p0);
             const bool steady = p0 >= first_out && nrows == RB;
+            const bool filling = p0 + nrows <= first_out;
 
             // MULTI: the earlier chunks' `best` of the rows this block finishes, asked for now so that the loads
             // are back long before the stores that depend on them (they used to be one exposed L2 round trip per row)
@@ -622,17 +682,17 @@ k_bitslice(BitsliceArgs a)
                 const uint32_t bw[2] = {__funnelshift_r(in.b[0], in.b[1], ls), __funnelshift_r(in.b[1], in.b[2], ls)};
                 const uint32_t vw[2] = {lw[0] | bw[0], lw[1] | bw[1]};
                 const unsigned long long vl = (((unsigned long long)vw[1]) << 32) | vw[0];
-                const bool all_valid = (~vl & ((1ull << STEPS) - 1ull)) == 0ull;
+                const bool all_valid = (~vl & ((1ull << (STEPS + (HP ? 16 : 0))) - 1ull)) == 0ull;
                 if (__all_sync(0xFFFFFFFFu, all_valid || !active)) {
-                    if (active) walk<HALF, NW, SEG, true>(q, lw, vw, hq, h5, mq);
+                    if (active) walk<HALF, NW, SEG, true, HP>(q, lw, vw, hq, h5, mq);
                 } else {
-                    if (active) walk<HALF, NW, SEG, false>(q, lw, vw, hq, h5, mq);
+                    if (active) walk<HALF, NW, SEG, false, HP>(q, lw, vw, hq, h5, mq);
                 }
             }
             __syncwarp();
 
             // prefetch the next block's walker inputs; they land while pass B runs
-            if (p0 + RB + wr < last_pr) load_walk_raw(in, a.h, p0 + RB + wr, rbit, lbit);
+            if (p0 + nrows + wr < last_pr) load_walk_raw(in, a.h, p0 + nrows + wr, rbit, lbit);
 
             // ---------------- pass B: 32 pixel columns ----------------
             if (steady) {
@@ -682,8 +742,33 @@ k_bitslice(BitsliceArgs a)
                     }
                     finish_rows(std::integral_constant<int, G>{}, Vs, Ms, prev + r);
                 }
+            } else if (filling) {
+                // the window is still filling and no row of this block completes an output row: the rows enter the
+                // ring and the sums, nothing leaves, nothing is stored
+                if (nrows == RB) {
+#pragma unroll
+                    for (int r = 0; r < RB; r++) {
+                        uint32_t hn[NW][5], en[EC];
+#pragma unroll
+                        for (int w = 0; w < NW; w++) load_h(r, w, hn[w]);
+                        to_cols(hn, en);
+                        tm_store<EC>(tring + wrap_t(tslot + r) * EC, en);
+#pragma unroll
+                        for (int w = 0; w < NW; w++) planes_add<PV, KH>(V[w], hn[w]);
+                    }
+                } else {
+                    for (int r = 0; r < nrows; r++) {
+                        uint32_t hn[NW][5], en[EC];
+#pragma unroll
+                        for (int w = 0; w < NW; w++) load_h(r, w, hn[w]);
+                        to_cols(hn, en);
+                        tm_store<EC>(tring + wrap_t(tslot + r) * EC, en);
+#pragma unroll
+                        for (int w = 0; w < NW; w++) planes_add<PV, KH>(V[w], hn[w]);
+                    }
+                }
             } else {
-                // warm-up rows (window still filling) and the ragged last block
+                // the ragged last block of a run
                 for (int r = 0; r < nrows; r++) {
                     const int pr = p0 + r;
                     uint32_t hn[NW][5], ho[NW][5];
@@ -736,7 +821,7 @@ k_bitslice(BitsliceArgs a)
     }
 }
 
-template <int HALF, int NW, int SEG, bool C2>
+template <int HALF, int NW, int SEG, bool C2, bool HP>
 int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
 {
     using C = WS<HALF, NW, SEG>;
@@ -748,8 +833,13 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
         set_error("bit-sliced kernel: %d shifts need two shift words per lane", h.g.D);
         return SM_ERR_ARG;
     }
-    auto kern = C2 ? k_bitslice<HALF, NW, SEG, false, C2>
-                   : (multi ? k_bitslice<HALF, NW, SEG, NW == 2, false> : k_bitslice<HALF, NW, SEG, false, false>);
+    if (HP && h.g.D > 16) {
+        set_error("bit-sliced kernel: half-word pairs hold at most 16 shifts, not %d", h.g.D);
+        return SM_ERR_ARG;
+    }
+    auto kern = (C2 || HP) ? k_bitslice<HALF, NW, SEG, false, C2, HP>
+                           : (multi ? k_bitslice<HALF, NW, SEG, NW == 2 && !HP, false, false>
+                                    : k_bitslice<HALF, NW, SEG, false, false, false>);
     // resident warps per SM of this instantiation: what shared memory, the 512 TMEM columns and the register file
     // allow, all known at compile time (WS::CTAS_PER_SM is also the kernel's __launch_bounds__).  (The occupancy
     // API is not asked: it answers 1 CTA per SM for these kernels, whatever carve-out is set, while the
@@ -762,7 +852,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
     if (mode == MODE_PREPARE) return warps_per_sm;  // module loaded, attribute set
     BitsliceArgs a;
     a.h = h;
-    const int strip_cols = C2 ? C::TW * NW : C::TW;
+    const int strip_cols = C::TW * (C2 ? NW : 1) * (HP ? 2 : 1);
     const int strips = (h.g.W + strip_cols - 1) / strip_cols;
     // a run is at least one block of rows.  (Short runs pay 2*half warm-up rows each, but they
     // only happen when the frame is too small to fill the machine, where latency is what counts.)
@@ -784,13 +874,14 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
         segs = h.force_segs;  // development hook (sm_set_option)
     } else if (h.npairs == 1) {
         // latency mode (one pair per launch).  All CTAs do the same work: a run of R rows costs R + 2*half
-        // window-filling rows + a fixed start-up.  The kernel is bound by the ALU pipe, so an SM takes as long as
+        // window-filling rows (about half a row each) + a fixed start-up.  The kernel is bound by the ALU pipe, so an SM takes as long as
         // the work of the CTAs that land on it (they are dealt round-robin: ceil(CTAs / SMs) on the fullest),
         // stretched when too few warps are resident to keep the pipe busy (measured: about 55 % of the pipe
         // with 4 warps per SM, 93 % with 8, flat from 12).  Pick the number of runs that minimises that
         // (short runs pay more filling rows, long runs leave SMs idle or thin); a cost model instead of
         // timing candidates at sm_create.
         const int start_rows = 4;
+        const double fill_weight = 0.5;  // a window-filling row: pass A and one add, no subtraction, no winner-take-all
         double best_cost = -1.0;
         segs = 1;
         for (int sg = 1; sg <= max_segs; sg++) {
@@ -800,7 +891,7 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
             const int per_sm = (ctas + num_sms - 1) / num_sms;
             const int resident = (per_sm < C::CTAS_PER_SM ? per_sm : C::CTAS_PER_SM) * C::WPC;
             const double eff = resident >= 12 ? 1.0 : (resident <= 4 ? 0.55 : 0.55 + 0.45 * (resident - 4) / 8.0);
-            const double cost = per_sm * (double)(rows + 2 * HALF + start_rows) / eff;
+            const double cost = per_sm * (rows + fill_weight * 2 * HALF + start_rows) / eff;
             if (best_cost < 0 || cost < best_cost) best_cost = cost, segs = got;
             if (ctas > 6 * slots) break;
         }
@@ -843,7 +934,8 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
 //          Measured on config 2 (us per pair, batched): 8 -> 18.2, 16 -> 18.0, 32 -> 25.2.
 struct Shape {
     int nw, seg;
-    bool c2;
+    bool c2, hp;
+    int strip_cols() const { return 32 * (c2 ? nw : 1) * (hp ? 2 : 1); }
 };
 
 constexpr int C2_MAX_HALF = 6;
@@ -852,15 +944,19 @@ static Shape pick_shape(const HotArgs &h)
 {
     Shape sh;
     sh.seg = 16;
+    sh.hp = false;
     if (h.g.D > 32) {
         sh.nw = 2;
         sh.c2 = false;
     } else {
         sh.c2 = h.g.W >= 64 && h.g.half <= C2_MAX_HALF;
         sh.nw = sh.c2 ? 2 : 1;
+        // 16 shifts or fewer: two pixels per word (half-word pairs)
+        sh.hp = h.g.D <= 16 && h.g.W >= 64;
     }
 #ifdef SMB_DEV  // experiment hooks of the development build only (make DEV=1); never in the shipped library
     if (getenv("SMB_NO_C2") && atoi(getenv("SMB_NO_C2")) && sh.c2) sh.c2 = false, sh.nw = 1;
+    if (getenv("SMB_NO_HP") && atoi(getenv("SMB_NO_HP"))) sh.hp = false;
     if (getenv("SMB_NW") && !sh.c2) sh.nw = atoi(getenv("SMB_NW"));
     if (getenv("SMB_SEG")) sh.seg = atoi(getenv("SMB_SEG"));
 #endif
@@ -871,17 +967,21 @@ static int dispatch(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
 {
     const Shape sh = pick_shape(h);
     const int half = h.g.half;
-#define SM_SHAPE(HF, NW_, SEG_, C2_) \
-    if (half == HF && sh.nw == NW_ && sh.seg == SEG_ && sh.c2 == C2_) \
-        return launch_one<HF, NW_, SEG_, C2_>(h, num_sms, s, mode);
+#define SM_SHAPE(HF, NW_, SEG_, C2_, HP_) \
+    if (half == HF && sh.nw == NW_ && sh.seg == SEG_ && sh.c2 == C2_ && sh.hp == HP_) \
+        return launch_one<HF, NW_, SEG_, C2_, HP_>(h, num_sms, s, mode);
 #define SM_HALVES(M, ...) \
     M(0, __VA_ARGS__) M(1, __VA_ARGS__) M(2, __VA_ARGS__) M(3, __VA_ARGS__) M(4, __VA_ARGS__) M(5, __VA_ARGS__) \
     M(6, __VA_ARGS__) M(7, __VA_ARGS__) M(8, __VA_ARGS__) M(9, __VA_ARGS__) M(10, __VA_ARGS__) M(11, __VA_ARGS__) \
     M(12, __VA_ARGS__) M(13, __VA_ARGS__) M(14, __VA_ARGS__) M(15, __VA_ARGS__)
-    SM_HALVES(SM_SHAPE, 1, 16, false)
-    SM_HALVES(SM_SHAPE, 2, 16, false)
-    SM_SHAPE(0, 2, 16, true) SM_SHAPE(1, 2, 16, true) SM_SHAPE(2, 2, 16, true) SM_SHAPE(3, 2, 16, true)
-    SM_SHAPE(4, 2, 16, true) SM_SHAPE(5, 2, 16, true) SM_SHAPE(6, 2, 16, true)
+    SM_HALVES(SM_SHAPE, 1, 16, false, false)
+    SM_HALVES(SM_SHAPE, 2, 16, false, false)
+    SM_HALVES(SM_SHAPE, 1, 16, false, true)
+#define SM_C2(HP_) \
+    SM_SHAPE(0, 2, 16, true, HP_) SM_SHAPE(1, 2, 16, true, HP_) SM_SHAPE(2, 2, 16, true, HP_) SM_SHAPE(3, 2, 16, true, HP_) \
+    SM_SHAPE(4, 2, 16, true, HP_) SM_SHAPE(5, 2, 16, true, HP_) SM_SHAPE(6, 2, 16, true, HP_)
+    SM_C2(false) SM_C2(true)
+#undef SM_C2
 #undef SM_HALVES
 #undef SM_SHAPE
     set_error("bit-sliced kernel: window half %d with %d word(s) per lane and %d-column walks is not instantiated",
@@ -904,7 +1004,7 @@ int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s) { return disp
 int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 {
     // enough pairs that one launch is about three waves of the warps the SMs hold (HotArgs::blocks_per_sm)
-    const int strip_cols = pick_shape(h).c2 ? 64 : 32;
+    const int strip_cols = pick_shape(h).strip_cols();
     const int N = 2 * h.g.half + 1, strips = (h.g.W + strip_cols - 1) / strip_cols;
     const int want = throughput_run_windows() * N;
     const int segs = (h.g.BH + want - 1) / want > 0 ? (h.g.BH + want - 1) / want : 1;

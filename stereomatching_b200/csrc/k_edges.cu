@@ -132,6 +132,42 @@ __device__ __forceinline__ int lut_bit(const uint32_t *__restrict__ lut, int L, 
     return (__ldg(lut + L * LUT_WORDS + (R >> 5)) >> (R & 31)) & 1;
 }
 
+// The table as thresholds.  The detector is symmetric in its two sums (|l - r| and (l + r) / 2 are), and for a
+// fixed smaller sum m the decision is monotone in the larger one: no edge up to some hi[m], edge above it.  So
+//     edge(L, R) = max(L, R) > hi[min(L, R)]
+// and the 73 KB bit table (four scattered global loads per pixel) shrinks to 766 sixteen-bit entries that live in
+// shared memory.  k_edge_thresholds derives hi[] FROM the bit table and CHECKS both properties against every one
+// of its 766 x 766 bits; the flag word it leaves behind tells the detector kernels whether the thresholds stand
+// in for the table exactly (they fall back to the bit table otherwise).  Layout behind the bit table:
+// [LUT_N * LUT_WORDS] bits | [HI_WORDS] hi[] as u16 pairs | [1] flag.
+constexpr int HI_WORDS = (LUT_N + 1) / 2;
+constexpr int LUT_HI = LUT_N * LUT_WORDS, LUT_FLAG = LUT_HI + HI_WORDS;
+
+__global__ void k_edge_thresholds_init(uint32_t *__restrict__ lut) { lut[LUT_FLAG] = 1u; }
+
+__global__ void __launch_bounds__(256) k_edge_thresholds(uint32_t *__restrict__ lut)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= LUT_N) return;
+    int hi = LUT_N - 1;
+    for (int R = m; R < LUT_N; R++)
+        if (lut_bit(lut, m, R)) {
+            hi = R - 1;
+            break;
+        }
+    bool ok = hi >= m - 1;
+    for (int R = 0; R < LUT_N; R++) {
+        const int b = lut_bit(lut, m, R);
+        ok = ok && b == lut_bit(lut, R, m);          // symmetric
+        if (R >= m) ok = ok && b == (R > hi ? 1 : 0);  // monotone above the diagonal
+    }
+    reinterpret_cast<uint16_t *>(lut + LUT_HI)[m] = (uint16_t)(hi < 0 ? 0 : hi);
+    // hi = m - 1 (an edge already at L == R) cannot be told from hi = m at m = 0 once clamped: no such detector
+    // exists (|l - r| = 0 is never above a non-negative limit), and the check keeps it honest
+    if (hi < m) ok = false;
+    if (!ok) atomicAnd(lut + LUT_FLAG, 0u);
+}
+
 // one pixel, any position: wraps (WRAP) or falls back to FP64 with the 128.0 ghost cells (GHOST border)
 template <int VARIANT>
 __device__ __forceinline__ int edge_pixel(const uint8_t *__restrict__ img, int W, int FH, int x, int y, double thr,
@@ -234,6 +270,34 @@ k_edges_lut(const uint8_t *__restrict__ img, int W, int FH, int ystart, int nrow
 // invalid).  It stands in for k_edges_lut + k_pack: one launch and 4 B per pixel of traffic less.  Thread =
 // 4 consecutive pixels of one image; eight threads' nibbles are OR-reduced into a 32-pixel word by shuffles.
 // WRITE_U8: also store the byte maps (in-image pixels only), for sm_download(SM_EDGES*) and the debug planes.
+constexpr int EP_ROWS = 8;  // padded rows per block of k_edges_planes
+
+// detector decisions of 4 consecutive pixels from their 3 x 6 neighbourhood p[row][x4-1 .. x4+4]
+template <typename F>
+__device__ __forceinline__ uint32_t edge_nibble(const int (&p)[3][6], F &&edge)
+{
+    uint32_t e = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int tl = p[0][k], tc = p[0][k + 1], tr = p[0][k + 2];
+        const int ml = p[1][k], mr = p[1][k + 2];
+        const int bl = p[2][k], bc = p[2][k + 1], br = p[2][k + 2];
+        const int b = edge(tl + ml + bl, tr + mr + br) | edge(tl + tc + tr, bl + bc + br) |
+                      edge(tl + tc + ml, mr + bc + br) | edge(bl + bc + ml, tc + tr + mr);
+        e |= (uint32_t)b << k;
+    }
+    return e;
+}
+
+__device__ __forceinline__ void unpack_row(const uint8_t *__restrict__ row, int x4, int (&p)[6])
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(row + x4);
+    const uint32_t a = __ldg(w - 1), b = __ldg(w), c = __ldg(w + 1);
+    p[0] = a >> 24;
+    p[1] = b & 255, p[2] = (b >> 8) & 255, p[3] = (b >> 16) & 255, p[4] = b >> 24;
+    p[5] = c & 255;
+}
+
 template <int VARIANT, bool WRITE_U8>
 __global__ void __launch_bounds__(128)
 k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img2, int FH, int row0, PackedGeom g,
@@ -244,6 +308,14 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
     // the hot kernel may be scheduled as this grid's programmatic dependent (it waits for completion before
     // it reads the planes)
     asm volatile("griddepcontrol.launch_dependents;");
+    __shared__ uint16_t hi_s[2 * HI_WORDS];
+    {
+        const uint32_t *src = lut + LUT_HI;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(hi_s);
+        for (int k = threadIdx.x; k < HI_WORDS; k += blockDim.x) dst[k] = __ldg(src + k);
+    }
+    const bool thresholds_exact = __ldg(lut + LUT_FLAG) != 0u;
+    __syncthreads();
     const int pair = blockIdx.z >> 1, side = blockIdx.z & 1;
     const uint8_t *img = (side ? img2 : img1) + (size_t)pair * image_stride;
     uint8_t *edges = WRITE_U8 ? (side ? edges2 : edges1) + (size_t)pair * image_stride : nullptr;
@@ -251,89 +323,147 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
     const int t = blockIdx.x * blockDim.x + threadIdx.x;  // thread <-> 4 pixels; 8 threads <-> one word
     const int wd = t >> 3;
     const int lane = threadIdx.x & 31;
-    const int pr = blockIdx.y;
-    int y = row0 - g.half + pr;
-    bool rowvalid = true;
-    if (VARIANT == SM_WRAP) {
-        y %= FH;
-        if (y < 0) y += FH;
-    } else {
-        rowvalid = y >= 0 && y < FH;
-    }
     const int x4 = t * 4 - PADL;
-    uint32_t e = 0, v = 0;
-    if (wd < g.WPR && rowvalid) {
-        int ym = y - 1, yp = y + 1;
+    const int pr0 = blockIdx.y * EP_ROWS, pr1 = min(g.ER, pr0 + EP_ROWS);
+    // WRAP: a padding pixel IS the wrapped image pixel, so the thread works at its wrapped column xs (when the
+    // width is a multiple of 4 its four pixels stay contiguous there).  Word path: the four pixels and their
+    // neighbours are inside the image and word-aligned; otherwise the 3 x 6 neighbourhood is gathered byte by byte
+    // through the wrap (WRAP) or the pixels are taken one by one (GHOST borders: FP64 with the 128.0 ghost cells).
+    int xs = x4;
+    if (VARIANT == SM_WRAP) {
+        xs %= W;
+        if (xs < 0) xs += W;
+    }
+    const bool xfast = wd < g.WPR && (W & 3) == 0 && xs >= 4 && xs + 8 <= W && (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+    auto frame_row = [&](int pr, bool &valid) {
+        int y = row0 - g.half + pr;
+        valid = true;
         if (VARIANT == SM_WRAP) {
-            ym = ym < 0 ? ym + FH : ym;
-            yp = yp >= FH ? yp - FH : yp;
-        }
-        const bool fast = ym >= 0 && yp < FH && (W & 3) == 0 && x4 >= 4 && x4 + 8 <= W &&
-                          (reinterpret_cast<uintptr_t>(img) & 3) == 0;
-        if (fast) {
-            int p[3][6];  // pixels x4-1 .. x4+4 of the three rows
-            const int ys[3] = {ym, y, yp};
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const uint32_t *w = reinterpret_cast<const uint32_t *>(img + (size_t)ys[j] * W + x4);
-                const uint32_t a = __ldg(w - 1), b = __ldg(w), c = __ldg(w + 1);
-                p[j][0] = a >> 24;
-                p[j][1] = b & 255, p[j][2] = (b >> 8) & 255, p[j][3] = (b >> 16) & 255, p[j][4] = b >> 24;
-                p[j][5] = c & 255;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int tl = p[0][k], tc = p[0][k + 1], tr = p[0][k + 2];
-                const int ml = p[1][k], mr = p[1][k + 2];
-                const int bl = p[2][k], bc = p[2][k + 1], br = p[2][k + 2];
-                const int b = lut_bit(lut, tl + ml + bl, tr + mr + br) | lut_bit(lut, tl + tc + tr, bl + bc + br) |
-                              lut_bit(lut, tl + tc + ml, mr + bc + br) | lut_bit(lut, bl + bc + ml, tc + tr + mr);
-                e |= (uint32_t)b << k;
-            }
-            v = 0xFu;
+            y %= FH;
+            if (y < 0) y += FH;
         } else {
+            valid = y >= 0 && y < FH;
+        }
+        return y;
+    };
+    auto edge_hi = [&](int L, int R) { return (int)(max(L, R) > (int)hi_s[min(L, R)]); };
+    auto edge_lut = [&](int L, int R) { return lut_bit(lut, L, R); };
+
+    int p[3][6];       // rows y-1, y, y+1 of the sliding window (xfast threads only)
+    int have_y = -2;   // p[1], p[2] hold rows have_y, have_y + 1 (unwrapped successor) when have_y >= 0
+    for (int pr = pr0; pr < pr1; pr++) {
+        bool rowvalid;
+        const int y = frame_row(pr, rowvalid);
+        uint32_t e = 0, v = 0;
+        if (wd < g.WPR && rowvalid) {
+            int ym = y - 1, yp = y + 1;
+            if (VARIANT == SM_WRAP) {
+                ym = ym < 0 ? ym + FH : ym;
+                yp = yp >= FH ? yp - FH : yp;
+            }
+            if (xfast && ym >= 0 && yp < FH) {
+                // consecutive padded rows are consecutive frame rows (mod FH): the window slides, one new row
+                // of three words per step
+                if (have_y == ym) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int x = x4 + k;
-                bool ok = true;
-                if (VARIANT == SM_WRAP) {
-                    x %= W;
-                    if (x < 0) x += W;
+                    for (int k = 0; k < 6; k++) p[0][k] = p[1][k], p[1][k] = p[2][k];
                 } else {
-                    ok = x >= 0 && x < W;
+                    unpack_row(img + (size_t)ym * W, xs, p[0]);
+                    unpack_row(img + (size_t)y * W, xs, p[1]);
                 }
-                if (ok) {
-                    e |= (uint32_t)edge_pixel<VARIANT>(img, W, FH, x, y, thr, lut) << k;
+                unpack_row(img + (size_t)yp * W, xs, p[2]);
+                have_y = y;
+                e = thresholds_exact ? edge_nibble(p, edge_hi) : edge_nibble(p, edge_lut);
+                v = 0xFu;
+            } else if (VARIANT == SM_WRAP) {
+                // at the seam, or a width that is no multiple of 4: every byte through the wrap, all 18 loads
+                // independent (one memory round trip per row, not one per pixel)
+                int xk[6];
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    int x = (x4 - 1 + k) % W;
+                    xk[k] = x < 0 ? x + W : x;
+                }
+                const int ys[3] = {ym, y, yp};
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) p[j][k] = __ldg(img + (size_t)ys[j] * W + xk[k]);
+                have_y = -2;
+                e = thresholds_exact ? edge_nibble(p, edge_hi) : edge_nibble(p, edge_lut);
+                v = 0xFu;
+            } else {
+                // GHOST, at the frame's border: gather the neighbourhood once (-1 = outside the frame, all loads
+                // independent), then per pixel the integer detector where its 3 x 3 stencil is inside and the FP64
+                // one with the 128.0 ghost cells (stereo-ghost.c:384-385) where it is not
+                have_y = -2;
+                const int ys[3] = {ym, y, yp};
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int k = 0; k < 6; k++) {
+                        const int x = x4 - 1 + k;
+                        const bool in = x >= 0 && x < W && ys[j] >= 0 && ys[j] < FH;
+                        p[j][k] = in ? (int)__ldg(img + (size_t)ys[j] * W + x) : -1;
+                    }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int x = x4 + k;
+                    if (x < 0 || x >= W) continue;
+                    int b;
+                    if ((p[0][k] | p[0][k + 1] | p[0][k + 2] | p[1][k] | p[1][k + 2] | p[2][k] | p[2][k + 1] | p[2][k + 2]) >= 0) {
+                        const int tl = p[0][k], tc = p[0][k + 1], tr = p[0][k + 2];
+                        const int ml = p[1][k], mr = p[1][k + 2];
+                        const int bl = p[2][k], bc = p[2][k + 1], br = p[2][k + 2];
+                        if (thresholds_exact)
+                            b = edge_hi(tl + ml + bl, tr + mr + br) | edge_hi(tl + tc + tr, bl + bc + br) |
+                                edge_hi(tl + tc + ml, mr + bc + br) | edge_hi(bl + bc + ml, tc + tr + mr);
+                        else
+                            b = edge_lut(tl + ml + bl, tr + mr + br) | edge_lut(tl + tc + tr, bl + bc + br) |
+                                edge_lut(tl + tc + ml, mr + bc + br) | edge_lut(bl + bc + ml, tc + tr + mr);
+                    } else {
+                        auto B = [&](int dx, int dy) {
+                            const int q = p[dy + 1][k + 1 + dx];
+                            return q < 0 ? 128.0 : to_bright<uint8_t>((uint8_t)q);
+                        };
+                        b = detect(B(-1, -1), B(-1, 0), B(-1, 1), B(1, -1), B(1, 0), B(1, 1), thr) |
+                            detect(B(-1, -1), B(0, -1), B(1, -1), B(-1, 1), B(0, 1), B(1, 1), thr) |
+                            detect(B(-1, -1), B(0, -1), B(-1, 0), B(1, 0), B(0, 1), B(1, 1), thr) |
+                            detect(B(-1, 1), B(0, 1), B(-1, 0), B(0, -1), B(1, -1), B(1, 0), thr);
+                    }
+                    e |= (uint32_t)b << k;
                     v |= 1u << k;
                 }
             }
-        }
-        if (WRITE_U8) {
-            // the byte maps hold the frame itself: only the unwrapped in-image pixels of this word
-            if (x4 >= 0 && x4 + 4 <= W && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(edges) & 3) == 0) {
-                *reinterpret_cast<uint32_t *>(edges + (size_t)y * W + x4) =
-                    (e & 1u) | ((e & 2u) << 7) | ((e & 4u) << 14) | ((e & 8u) << 21);
-            } else {
-                for (int k = 0; k < 4; k++)
-                    if (x4 + k >= 0 && x4 + k < W) edges[(size_t)y * W + x4 + k] = (uint8_t)((e >> k) & 1u);
+            if (WRITE_U8) {
+                // the byte maps hold the frame itself: only the unwrapped in-image pixels of this word
+                if (x4 >= 0 && x4 + 4 <= W && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(edges) & 3) == 0) {
+                    *reinterpret_cast<uint32_t *>(edges + (size_t)y * W + x4) =
+                        (e & 1u) | ((e & 2u) << 7) | ((e & 4u) << 14) | ((e & 8u) << 21);
+                } else {
+                    for (int k = 0; k < 4; k++)
+                        if (x4 + k >= 0 && x4 + k < W) edges[(size_t)y * W + x4 + k] = (uint8_t)((e >> k) & 1u);
+                }
             }
-        }
-    }
-    // eight threads' nibbles -> one 32-pixel word (all 32 lanes take part)
-    const int sh = 4 * (lane & 7);
-    uint32_t ew = e << sh, vw = v << sh;
-#pragma unroll
-    for (int m = 1; m <= 4; m <<= 1) {
-        ew |= __shfl_xor_sync(0xFFFFFFFFu, ew, m);
-        vw |= __shfl_xor_sync(0xFFFFFFFFu, vw, m);
-    }
-    if ((lane & 7) == 0 && wd < g.WPR) {
-        const size_t o = (size_t)pair * plane_stride + (size_t)pr * g.WPR + wd;
-        if (side == 0) {
-            LA[o] = ew & vw;
-            LB[o] = ~ew & vw;
         } else {
-            RB[o] = ew & vw;
+            have_y = -2;
+        }
+        // eight threads' nibbles -> one 32-pixel word (all 32 lanes take part)
+        const int sh = 4 * (lane & 7);
+        uint32_t ew = e << sh, vw = v << sh;
+#pragma unroll
+        for (int m = 1; m <= 4; m <<= 1) {
+            ew |= __shfl_xor_sync(0xFFFFFFFFu, ew, m);
+            vw |= __shfl_xor_sync(0xFFFFFFFFu, vw, m);
+        }
+        if ((lane & 7) == 0 && wd < g.WPR) {
+            const size_t o = (size_t)pair * plane_stride + (size_t)pr * g.WPR + wd;
+            if (side == 0) {
+                LA[o] = ew & vw;
+                LB[o] = ~ew & vw;
+            } else {
+                RB[o] = ew & vw;
+            }
         }
     }
 }
@@ -343,7 +473,7 @@ int launch_edges_planes(const uint8_t *img1, const uint8_t *img2, int FH, int ro
                         uint8_t *edges2, cudaStream_t s, int npairs, size_t image_stride, size_t plane_stride)
 {
     dim3 block(128);
-    dim3 grid((g.WPR * 8 + block.x - 1) / block.x, g.ER, 2 * npairs);
+    dim3 grid((g.WPR * 8 + block.x - 1) / block.x, (g.ER + EP_ROWS - 1) / EP_ROWS, 2 * npairs);
     const bool u8 = edges1 != nullptr && edges2 != nullptr;
 #define SM_EP(V, U) \
     k_edges_planes<V, U><<<grid, block, 0, s>>>(img1, img2, FH, row0, g, threshold, lut, LA, LB, RB, edges1, edges2, \
@@ -361,11 +491,13 @@ int launch_edges_planes(const uint8_t *img1, const uint8_t *img2, int FH, int ro
 int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s)
 {
     k_edge_lut<<<LUT_N, 32, 0, s>>>(threshold, lut);
+    k_edge_thresholds_init<<<1, 1, 0, s>>>(lut);
+    k_edge_thresholds<<<(LUT_N + 255) / 256, 256, 0, s>>>(lut);
     SM_CUDA(cudaGetLastError());
-    return 1;
+    return 3;
 }
 
-size_t edge_lut_words() { return (size_t)LUT_N * LUT_WORDS; }
+size_t edge_lut_words() { return (size_t)LUT_FLAG + 1; }
 
 int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
                      const uint32_t *lut, uint8_t *edges, cudaStream_t s, int n_images, size_t image_stride)
@@ -383,6 +515,8 @@ int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, i
 void warm_edges(int variant)
 {
     warm_kernel(k_edge_lut);
+    warm_kernel(k_edge_thresholds_init);
+    warm_kernel(k_edge_thresholds);
     if (variant == SM_WRAP) {
         warm_kernel(k_edges<uint8_t, SM_WRAP>);
         warm_kernel(k_edges<double, SM_WRAP>);

@@ -41,20 +41,30 @@ int launch_fill_web_holes_step(const int32_t *src, int32_t *dst, int W, int H, c
     return 1;
 }
 
-__global__ void k_minmax_init(int32_t *mm)
+// min and max of the web in ONE launch and without a host round trip before the contour kernel:
+// mm holds two (min, max) slots.  A call accumulates into slot `cur` with atomics and re-arms the OTHER slot
+// for the next call; that slot's last readers (the previous call's contour kernel and device-to-host copy) are
+// earlier in the stream.  Both slots are armed once at sm_create (launch_minmax_arm).
+__global__ void k_minmax_arm(int32_t *mm)
 {
-    mm[0] = INT_MAX;
-    mm[1] = INT_MIN;
+    mm[0] = mm[2] = INT_MAX;
+    mm[1] = mm[3] = INT_MIN;
 }
 
-__global__ void __launch_bounds__(256) k_minmax(const int32_t *__restrict__ a, size_t n, int32_t *mm)
+__global__ void __launch_bounds__(256) k_minmax(const int32_t *__restrict__ a, size_t n, int32_t *mm, int cur)
 {
     int32_t mn = INT_MAX, mx = INT_MIN;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        int32_t v = a[i];
-        mn = min(mn, v);
-        mx = max(mx, v);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+        const int4 *a4 = reinterpret_cast<const int4 *>(a);
+        for (size_t i = tid; i < n / 4; i += nth) {
+            const int4 v = a4[i];
+            mn = min(min(mn, v.x), min(min(v.y, v.z), v.w));
+            mx = max(max(mx, v.x), max(max(v.y, v.z), v.w));
+        }
+        for (size_t i = (n & ~(size_t)3) + tid; i < n; i += nth) mn = min(mn, a[i]), mx = max(mx, a[i]);
+    } else {
+        for (size_t i = tid; i < n; i += nth) mn = min(mn, a[i]), mx = max(mx, a[i]);
     }
     mn = __reduce_min_sync(0xFFFFFFFFu, mn);
     mx = __reduce_max_sync(0xFFFFFFFFu, mx);
@@ -70,35 +80,56 @@ __global__ void __launch_bounds__(256) k_minmax(const int32_t *__restrict__ a, s
             mn = min(mn, smn[k]);
             mx = max(mx, smx[k]);
         }
-        atomicMin(mm, mn);
-        atomicMax(mm + 1, mx);
+        atomicMin(mm + 2 * cur, mn);
+        atomicMax(mm + 2 * cur + 1, mx);
+        if (blockIdx.x == 0) {
+            mm[2 * (cur ^ 1)] = INT_MAX;
+            mm[2 * (cur ^ 1) + 1] = INT_MIN;
+        }
     }
 }
 
-int launch_minmax(const int32_t *a, size_t n, int32_t *d_minmax, cudaStream_t s)
+int launch_minmax_arm(int32_t *d_minmax, cudaStream_t s)
 {
-    k_minmax_init<<<1, 1, 0, s>>>(d_minmax);
-    int blocks = (int)((n + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (blocks < 1) blocks = 1;
-    k_minmax<<<blocks, 256, 0, s>>>(a, n, d_minmax);
+    k_minmax_arm<<<1, 1, 0, s>>>(d_minmax);
     SM_CUDA(cudaGetLastError());
-    return 2;
+    return 1;
 }
 
-// out = ((web - min) % interval) == 0   (stereo.cu:261-274)
+int launch_minmax(const int32_t *a, size_t n, int32_t *d_minmax, int cur, cudaStream_t s)
+{
+    int blocks = (int)((n / 4 + 255) / 256);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    k_minmax<<<blocks, 256, 0, s>>>(a, n, d_minmax, cur);
+    SM_CUDA(cudaGetLastError());
+    return 1;
+}
+
+// out = ((web - min) % interval) == 0 with interval = (max - min) / lines   (stereo.cu:261-285), min and max
+// read from the device slot the min/max kernel filled.  A zero interval (the reference divides by zero there,
+// stereo.c:265-272) writes nothing; the host sees the same min/max and reports it.
 __global__ void __launch_bounds__(256)
-k_contour(const int32_t *__restrict__ web, size_t n, int32_t mn, int32_t interval,
+k_contour(const int32_t *__restrict__ web, size_t n, const int32_t *__restrict__ mm, int lines,
           uint8_t *__restrict__ out)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = ((web[i] - mn) % interval) == 0;
+    const int32_t mn = mm[0], interval = (mm[1] - mn) / lines;
+    if (interval == 0) return;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n && ((reinterpret_cast<uintptr_t>(web) & 15) | (reinterpret_cast<uintptr_t>(out) & 3)) == 0) {
+        const int4 v = *reinterpret_cast<const int4 *>(web + i);
+        *reinterpret_cast<uchar4 *>(out + i) =
+            make_uchar4(((v.x - mn) % interval) == 0, ((v.y - mn) % interval) == 0, ((v.z - mn) % interval) == 0,
+                        ((v.w - mn) % interval) == 0);
+    } else {
+        for (size_t k = i; k < n && k < i + 4; k++) out[k] = ((web[k] - mn) % interval) == 0;
+    }
 }
 
-int launch_contour(const int32_t *web, size_t n, int32_t mn, int32_t interval, uint8_t *out,
+int launch_contour(const int32_t *web, size_t n, const int32_t *d_minmax_slot, int lines, uint8_t *out,
                    cudaStream_t s)
 {
-    k_contour<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(web, n, mn, interval, out);
+    k_contour<<<(unsigned)(((n + 3) / 4 + 255) / 256), 256, 0, s>>>(web, n, d_minmax_slot, lines, out);
     SM_CUDA(cudaGetLastError());
     return 1;
 }
@@ -128,7 +159,7 @@ int launch_i32_to_u8(const int32_t *src, uint8_t *dst, size_t n, cudaStream_t s)
 void warm_step3()
 {
     warm_kernel(k_fill_holes);
-    warm_kernel(k_minmax_init);
+    warm_kernel(k_minmax_arm);
     warm_kernel(k_minmax);
     warm_kernel(k_contour);
     warm_kernel(k_i32_to_u8);

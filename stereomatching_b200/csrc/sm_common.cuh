@@ -126,8 +126,9 @@ int launch_edges_planes(const uint8_t *img1, const uint8_t *img2, int FH, int ro
                         uint8_t *edges2, cudaStream_t s, int npairs = 1, size_t image_stride = 0, size_t plane_stride = 0);
 
 int launch_fill_web_holes_step(const int32_t *src, int32_t *dst, int W, int H, cudaStream_t s);
-int launch_minmax(const int32_t *a, size_t n, int32_t *d_minmax, cudaStream_t s);
-int launch_contour(const int32_t *web, size_t n, int32_t mn, int32_t interval, uint8_t *out,
+int launch_minmax_arm(int32_t *d_minmax, cudaStream_t s);
+int launch_minmax(const int32_t *a, size_t n, int32_t *d_minmax, int cur, cudaStream_t s);
+int launch_contour(const int32_t *web, size_t n, const int32_t *d_minmax_slot, int lines, uint8_t *out,
                    cudaStream_t s);
 int launch_i32_to_u8(const int32_t *src, uint8_t *dst, size_t n, cudaStream_t s);
 

@@ -72,7 +72,9 @@ struct sm_ctx {
     bool web_may_have_holes = false;          // only a web from sm_set_web can contain zeros
     uint8_t *out = nullptr;
     bool have_out = false;
-    int32_t *minmax = nullptr;
+    int32_t *minmax = nullptr;       // two (min, max) slots, used alternately (k_step3.cu)
+    int32_t *minmax_host = nullptr;  // pinned landing place of a slot
+    int minmax_cur = 0;
     // band-sized packed planes
     uint32_t *LA = nullptr, *LB = nullptr, *RB = nullptr;
     // sm_match_wta_dev_batch: a second stream packs pair k+1.. while the main kernel of
@@ -328,7 +330,9 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
     SM_REQUIRE(width > 0 && frame_height > 0, "sm_create: width/height must be positive");
     SM_REQUIRE((size_t)width * frame_height < ((size_t)1 << 31), "sm_create: frame too large");
     SM_REQUIRE(num_shifts >= 1 && num_shifts <= 512, "sm_create: num_shifts must be in [1, 512]");
-    SM_REQUIRE(square_width >= 1 && square_width <= 63, "sm_create: square_width must be in [1, 63]");
+    // the reference takes any square_width up to the frame size (stereo.cu:395-398); its window is
+    // half = square_width / 2 either side, so 0 (and -1) mean the 1x1 window.  Wider than 63 is not built here.
+    SM_REQUIRE(square_width >= -1 && square_width <= 63, "sm_create: square_width must be in [0, 63]");
     // same check as the reference driver (stereo.cu:395-398)
     SM_REQUIRE(square_width <= width && square_width <= frame_height,
                "sm_create: square width must not be higher than image width/height");
@@ -379,8 +383,13 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
     if ((rc = dev_alloc(&c->edges[0], 2 * n)) ||
         (rc = dev_alloc(&c->best, n)) || (rc = dev_alloc(&c->web, n)) ||
         (rc = dev_alloc(&c->LA, pw)) || (rc = dev_alloc(&c->LB, pw)) || (rc = dev_alloc(&c->RB, pw)) ||
-        (rc = dev_alloc(&c->minmax, 2)))
+        (rc = dev_alloc(&c->minmax, 4)))
         return fail(rc);
+    if (cudaHostAlloc((void **)&c->minmax_host, 2 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess) {
+        set_error("sm_create: pinned allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(SM_ERR_NOMEM);
+    }
+    if ((rc = launch_minmax_arm(c->minmax, c->stream)) < 0) return fail(rc);
     c->edges[1] = c->edges[0] + n;
     // whole-frame contexts run step 3 as well: its buffers belong to the untimed set-up, like
     // the allocations at the top of the reference's algorithm() (stereo.cu:299-306)
@@ -395,6 +404,16 @@ extern "C" int sm_create_band(sm_ctx **out, int device, int width, int frame_hei
         HotArgs a = hot_args(c, c->best, c->web);
         if ((rc = prepare_bitslice(a, c->num_sms)) < 0) return fail(rc);
         c->occ = rc;
+    }
+    // the detector's decision table depends on the threshold alone: build it for the reference's default
+    // (DEFAULT_THRESHOLD 0.15, stereo.cu:7) here, so that sm_edges at that threshold is one launch; another threshold
+    // rebuilds the table on first use
+    if ((rc = dev_alloc(&c->edge_lut, edge_lut_words()))) return fail(rc);
+    if ((rc = launch_edge_lut(0.15, c->edge_lut, c->stream)) < 0) return fail(rc);
+    c->lut_threshold = 0.15;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        set_error("sm_create: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(SM_ERR_CUDA);
     }
     *out = c;
     return SM_OK;
@@ -424,6 +443,7 @@ extern "C" int sm_destroy(sm_ctx *c)
             if (e) cudaEventDestroy(e);
     }
     if (c->edge_lut) cudaFree(c->edge_lut);
+    if (c->minmax_host) cudaFreeHost(c->minmax_host);
     void *ptrs[] = {c->img_u8[0], nullptr,      c->img_f64[0], c->img_f64[1], c->edges[0], nullptr,  // [1] = [0] + npix
                     c->best,      c->web,       c->web2,       c->tmp,        c->out,      c->minmax,
                     c->LA,        c->LB,        c->RB,         c->scratch_u8, c->scratch_i32};
@@ -500,6 +520,13 @@ extern "C" int sm_get_info(sm_ctx *c, int what)
     case SM_INFO_WARPS_PER_SM: return c->occ;
     case SM_INFO_PAIRS_PER_LAUNCH: return c->batch_group_cap;
     case SM_INFO_TMEM_COLUMNS: return bitslice_supports(c->half, c->D) ? bitslice_tmem_columns(hot_args(c, c->best, c->web)) : 0;
+    case SM_INFO_EDGE_THRESHOLDS: {
+        if (!c->edge_lut || c->lut_threshold < 0.0) return -1;
+        uint32_t flag = 0;
+        SM_CUDA(cudaMemcpyAsync(&flag, c->edge_lut + edge_lut_words() - 1, sizeof flag, cudaMemcpyDeviceToHost, c->stream));
+        SM_CUDA(cudaStreamSynchronize(c->stream));
+        return flag != 0u;
+    }
     default: set_error("sm_get_info: unknown item %d", what); return SM_ERR_ARG;
     }
 }
@@ -865,10 +892,16 @@ extern "C" int sm_draw_contour_map(sm_ctx *c, int lines, int32_t *web_min, int32
     const int32_t *web = c->have_web2 ? c->web_filled : c->web;
     int rc;
     if ((rc = dev_alloc(&c->out, c->npix()))) return rc;
-    if ((rc = launch_minmax(web, c->npix(), c->minmax, c->stream)) < 0) return rc;
-    int32_t mm[2];
-    SM_CUDA(cudaMemcpyAsync(mm, c->minmax, sizeof mm, cudaMemcpyDeviceToHost, c->stream));
+    // min/max, its copy to the host and the contour kernel are queued back to back: the kernel takes min and max
+    // from the device slot, the host only needs them for the caller and for the degenerate case
+    const int cur = c->minmax_cur;
+    c->minmax_cur ^= 1;
+    const int32_t *slot = c->minmax + 2 * cur;
+    if ((rc = launch_minmax(web, c->npix(), c->minmax, cur, c->stream)) < 0) return rc;
+    SM_CUDA(cudaMemcpyAsync(c->minmax_host, slot, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (lines != 0 && (rc = launch_contour(web, c->npix(), slot, lines, c->out, c->stream)) < 0) return rc;
     SM_CUDA(cudaStreamSynchronize(c->stream));
+    const int32_t mm[2] = {c->minmax_host[0], c->minmax_host[1]};
     if (web_min) *web_min = mm[0];
     if (web_max) *web_max = mm[1];
     // interval = (max - min) / num_lines (stereo.cu:276-285 -> stereo.c:265-266)
@@ -877,8 +910,6 @@ extern "C" int sm_draw_contour_map(sm_ctx *c, int lines, int32_t *web_min, int32
                   "zero here", mm[1], mm[0], lines);
         return SM_ERR_DEGENERATE;
     }
-    if ((rc = launch_contour(web, c->npix(), mm[0], (mm[1] - mm[0]) / lines, c->out, c->stream)) < 0)
-        return rc;
     c->have_out = true;
     return SM_OK;
 }

@@ -12,6 +12,7 @@ from bench import synth_pair
 
 W, H, D, sw = 7680, 4320, 64, 9
 half = sw // 2
+all_ok = True
 orc = oracle.Oracle()
 left, right, disp = synth_pair(1234, W, H, D)
 for variant in (smb.WRAP, smb.GHOST):
@@ -32,5 +33,8 @@ for variant in (smb.WRAP, smb.GHOST):
     for band in range(3):
         with smb.StereoContext(W, H, D, sw, variant, rows=smb.band_rows(H, 3, band)) as c:
             c.upload_u8(left, right); c.edges(0.15); c.match_wta(); c.download(smb.WEB, out=web_b)
+    bands_ok = bool(np.array_equal(web_b, web))
+    all_ok = all_ok and ok and bands_ok
     print("%s 7680x4320 D=%d sw=%d: hot path %.3f ms = %.2f T MDE/s; slabs == oracle: %s; 3 bands == whole: %s"
-          % ("ghost" if variant else "wrap", D, sw, ms, W * H * D / ms / 1e9, ok, bool(np.array_equal(web_b, web))))
+          % ("ghost" if variant else "wrap", D, sw, ms, W * H * D / ms / 1e9, ok, bands_ok))
+sys.exit(0 if all_ok else 1)

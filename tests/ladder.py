@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/ladder.py -- the reference's published size ladder (report/data.txt:1-4: six sizes x four programs,
+"""tests/ladder.py (under tests/: it runs the reference's own CUDA programs from the oracle directory as the baseline) -- the reference's published size ladder (report/data.txt:1-4: six sizes x four programs,
 measured by test/time.sh:1-15) on this box: whole `algorithm()` elapsed of
 
   this repo's  timing/stereopar, timing/stereopar-ghost                (C drivers over the C ABI)
@@ -8,7 +8,7 @@ measured by test/time.sh:1-15) on this box: whole `algorithm()` elapsed of
 
 on the five fixtures of test/imgs plus a synthetic 7680x4320 pair (the ladder's sixth size, which the reference
 does not ship), with time.sh's parsing (field 15 of the stdout line) and the reference defaults (threshold 0.15,
-window 21, 30 shifts).  Writes a markdown table.  Run under gpurun: python tools/ladder.py > gpurun_out/ladder.md
+window 21, 30 shifts).  Writes a markdown table.  Run under gpurun: python tests/ladder.py > gpurun_out/ladder.md
 """
 import os
 import struct

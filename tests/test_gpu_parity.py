@@ -86,6 +86,35 @@ def test_f64_upload_is_the_reference_layout(orc):
                 assert np.array_equal(e1, orc.edges(a, thr, variant))
 
 
+def test_edge_detector_thresholds_and_odd_frames(orc):
+    """The 8-bit detector works from a threshold table derived from (and checked bit by bit against) the table of
+    FP64 decisions: it must report itself exact for every threshold tried, and edges of random images of odd sizes
+    (widths that are no multiple of 4, frames of one or two rows/columns, row bands) must equal the oracle's."""
+    rng = np.random.default_rng(11)
+    for variant in (smb.WRAP, smb.GHOST):
+        for (w, h) in [(64, 48), (67, 33), (1, 9), (2, 2), (5, 1), (130, 3), (257, 40), (640, 25)]:
+            a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+            b = np.where(rng.random((h, w)) < 0.8, 128, rng.integers(0, 256, (h, w))).astype(np.uint8)
+            for thr in (0.0, 0.03, THRESHOLD, 0.5, 1.0):
+                with _ctx(w, h, 8, 1, variant) as c:
+                    c.upload_u8(a, b)
+                    c.edges(thr)
+                    assert c.get_info(smb.INFO_EDGE_THRESHOLDS) == 1, thr
+                    assert np.array_equal(c.download(smb.EDGES1), orc.edges(a, thr, variant)), (w, h, thr)
+                    assert np.array_equal(c.download(smb.EDGES2), orc.edges(b, thr, variant)), (w, h, thr)
+        # a row band: the planes the detector writes feed the hot path directly
+        a = rng.integers(0, 256, (90, 200), dtype=np.uint8)
+        b = np.roll(a, 3, axis=1)
+        e1, e2 = orc.edges(a, THRESHOLD, variant), orc.edges(b, THRESHOLD, variant)
+        bo, wo = orc.match_wta(e1, e2, 20, 7, variant)
+        web = np.zeros((90, 200), np.int32)
+        for band in range(3):
+            with smb.StereoContext(200, 90, 20, 7, variant, rows=smb.band_rows(90, 3, band)) as c:
+                c.upload_u8(a, b), c.edges(THRESHOLD), c.match_wta()
+                c.download(smb.WEB, out=web)
+        assert np.array_equal(web, wo)
+
+
 # ---------------------------------------------------------------------------------
 # synthetic config 2 (the bench workload) and the parameter sweep
 # ---------------------------------------------------------------------------------
@@ -129,7 +158,7 @@ def test_golden_sweep(orc, golden, kernel):
 GEOMS = [  # (w, h, D, sw): odd widths, W not a multiple of 16/32, sw == min(w,h), D > W
     (21, 21, 30, 21), (33, 17, 7, 3), (64, 64, 64, 9), (100, 37, 30, 21), (257, 33, 40, 5),
     (130, 70, 130, 11), (48, 48, 512, 7), (19, 40, 64, 9), (512, 24, 33, 13), (96, 50, 1, 1),
-    (200, 45, 96, 15), (77, 31, 31, 17), (640, 40, 256, 11), (35, 35, 65, 2),
+    (200, 45, 96, 15), (77, 31, 31, 17), (640, 40, 256, 11), (35, 35, 65, 2), (96, 50, 7, 0), (70, 20, 40, 0),
     # windows 23..31: still the bit-sliced kernel (5 row-count planes, 10 box-count planes)
     (120, 60, 40, 23), (90, 90, 64, 27), (200, 64, 30, 31), (310, 35, 100, 29), (64, 31, 20, 31), (70, 66, 33, 25),
 ]
@@ -149,6 +178,38 @@ def test_random_edge_maps_odd_geometries(orc, variant, kernel):
             best, web = _run_edges(c, le, re)
         assert np.array_equal(best, bo), (w, h, D, sw)
         assert np.array_equal(web, wo), (w, h, D, sw)
+
+
+HP_GEOMS = [  # 16 shifts or fewer: two pixels per match word (half-word pairs), with and without column pairs
+    (64, 40, 16, 9), (65, 33, 16, 13), (127, 50, 9, 3), (128, 41, 1, 1), (129, 37, 16, 15), (200, 60, 12, 21),
+    (333, 45, 16, 7), (256, 64, 5, 11), (1000, 30, 16, 5), (191, 70, 2, 31), (70, 70, 16, 17), (640, 33, 15, 13),
+]
+
+
+@pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)
+def test_half_word_pairs(orc, variant):
+    for gi, (w, h, D, sw) in enumerate(HP_GEOMS):
+        rng = np.random.default_rng(2000 + gi)
+        dens = [0.05, 0.3, 0.5, 0.9][gi % 4]
+        le = (rng.random((h, w)) < dens).astype(np.uint8)
+        re = np.roll(le, rng.integers(0, max(1, min(D, w))), axis=1)
+        re ^= (rng.random((h, w)) < 0.02).astype(np.uint8)
+        bo, wo = orc.match_wta(le, re, D, sw, variant)
+        with _ctx(w, h, D, sw, variant, smb.KERNEL_BITSLICE) as c:
+            best, web = _run_edges(c, le, re)
+            # several pairs per launch take the throughput shape of the same kernel
+            import torch
+            n = 3
+            d1 = torch.from_numpy(np.stack([le] * n)).cuda()
+            d2 = torch.from_numpy(np.stack([re] * n)).cuda()
+            bb = torch.zeros((n, h, w), dtype=torch.int32, device="cuda")
+            ww = torch.zeros_like(bb)
+            c.match_wta_dev_batch(n, d1.data_ptr(), d2.data_ptr(), h * w, bb.data_ptr(), ww.data_ptr(), h * w)
+            c.synchronize()
+        assert np.array_equal(best, bo), (w, h, D, sw)
+        assert np.array_equal(web, wo), (w, h, D, sw)
+        for k in range(n):
+            assert np.array_equal(bb[k].cpu().numpy(), bo) and np.array_equal(ww[k].cpu().numpy(), wo), (w, h, D, sw, k)
 
 
 def test_windows_beyond_the_bitsliced_kernel(orc):
@@ -506,6 +567,16 @@ def test_fuzz_sample():
     import sys
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz_gpu.py"), "60", "99"],
                        capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_big_frame_8k():
+    """tests/big_frame_check.py: a 7680x4320 pair (the ladder's largest size, report/data.txt), both variants: slabs
+    against the oracle and three row bands against the whole frame."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "big_frame_check.py")],
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, call 11: size ladder, ncu evidence for the window-21 kernels and the config-2 batch, config-5 sweep
 O=gpurun_out
-python tools/ladder.py 3 > $O/c11_ladder.md 2> $O/c11_ladder.err; cat $O/c11_ladder.md; tail -n 3 $O/c11_ladder.err
+python tests/ladder.py 3 > $O/c11_ladder.md 2> $O/c11_ladder.err; cat $O/c11_ladder.md; tail -n 3 $O/c11_ladder.err
 python tools/batch_fixture.py > $O/c11_batch_fixture.log 2>&1; cat $O/c11_batch_fixture.log
 for p in c4 ref30 c2; do
 python tools/exp_shapes.py $p --default-only > $O/c11_plain_$p.log 2>&1 && \

@@ -2,7 +2,8 @@
 """Split the SASS page of an ncu report into regions of equal execution count (loop bodies, straight-line code)
 and print, per region, the executed warp instructions by pipe class, the stall samples and their top reasons.
 
-usage: python tools/sass_regions.py report.ncu-rep [kernel-index]
+usage: python tools/sass_regions.py report.ncu-rep [kernel-index] [--dump REGION[:LINES]]
+       --dump prints the SASS of one region (first LINES instructions, default 120) as a committed excerpt
 """
 import collections
 import csv
@@ -17,7 +18,11 @@ LSU = {"LDS", "STS", "LDG", "STG", "LDSM", "LD", "ST", "LDC", "LDCU", "ULDC"}
 
 def main():
     path = sys.argv[1]
-    which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    which = int(sys.argv[2]) if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else 0
+    dump = None
+    if "--dump" in sys.argv:
+        d = sys.argv[sys.argv.index("--dump") + 1].split(":")
+        dump = (int(d[0]), int(d[1]) if len(d) > 1 else 120)
     out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source", "sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -40,8 +45,10 @@ def main():
             continue
         op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
         if cur is None or cur["n"] != n:
-            cur = {"n": n, "len": 0, "ops": collections.Counter(), "samples": 0, "stalls": collections.Counter()}
+            cur = {"n": n, "len": 0, "ops": collections.Counter(), "samples": 0, "stalls": collections.Counter(),
+                   "text": []}
             regions.append(cur)
+        cur["text"].append(r[iS])
         cur["len"] += 1
         cur["ops"][op] += 1
         cur["samples"] += int(r[iN] or 0)
@@ -63,6 +70,15 @@ def main():
         ops = ", ".join("%s %d" % kv for kv in r["ops"].most_common(6))
         print("| %d | %d | %d | %.1f %% | %d | %d | %d | %d | %.1f %% | %s | %s |"
               % (k, r["n"], r["len"], 100.0 * ex / tot, a, f, l, r["len"] - a - f - l, 100.0 * r["samples"] / max(1, tots), st, ops))
+
+
+    if dump:
+        k, nl = dump
+        print("\nSASS of region %d (executed %d times per warp-instruction slot), first %d of %d instructions:\n\n```"
+              % (k, regions[k]["n"], min(nl, regions[k]["len"]), regions[k]["len"]))
+        for t in regions[k]["text"][:nl]:
+            print(t)
+        print("```")
 
 
 if __name__ == "__main__":
