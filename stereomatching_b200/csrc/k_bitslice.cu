@@ -420,10 +420,18 @@ __device__ __forceinline__ void wta(const uint32_t (&V)[NR_][NW][PV], const uint
     }
 }
 
-__device__ __forceinline__ void store_if(int32_t *p, int v, bool on)
+// lane_base[row * row_bytes / 4 + OFF] = v where `on`: lane_base is the lane's own column of the output array, so the
+// address is ONE widening multiply-add with a per-thread addend (IMAD.WIDE on the FMA pipe, which has room) and the
+// column offset rides in the store's immediate field -- no shift / add / add-with-carry on the ALU pipe, which
+// binds this kernel.
+template <int OFF>
+__device__ __forceinline__ void store_if(int32_t *lane_base, int row, int row_bytes, int v, bool on)
 {
-    asm volatile("{ .reg .pred q; setp.ne.s32 q, %2, 0; @q st.global.b32 [%0], %1; }" ::"l"(p), "r"(v), "r"((int)on)
-                 : "memory");
+    asm volatile(
+        "{ .reg .pred q; .reg .u64 ad; setp.ne.s32 q, %4, 0; mad.wide.s32 ad, %1, %2, %0; @q st.global.b32 [ad+%5], %3; }" ::"l"(
+            lane_base),
+        "r"(row), "r"(row_bytes), "r"(v), "r"((int)on), "n"(4 * OFF)
+        : "memory");
 }
 
 // C2 ("column pairs", for num_shifts <= 32): the NW = 2 words of a lane are not two shift words of one pixel but
@@ -556,9 +564,10 @@ k_bitslice(BitsliceArgs a)
         WalkRaw in = {};
         if (ja + wr < last_pr) load_walk_raw(in, a.h, ja + wr, rbit, lbit);
         int mslot0 = 0;  // centre-match ring slot of padded row p0
-        // next output row, as a 32-bit element offset (frames are < 2^31 pixels): the address
-        // arithmetic then is one multiply-add per store (FMA pipe) instead of 64-bit pointer adds
-        int oidx = (a.h.row0 + ja) * g.W + ximg;
+        // next output row of the frame, and the lane's own column of the two output arrays
+        int orow = a.h.row0 + ja;
+        const int row_bytes = 4 * g.W;
+        int32_t *const lane_best = a.h.best + ximg, *const lane_web = a.h.web + ximg;
 
         // store a finished row (best, idx) and advance the output pointers.  MULTI: a later chunk holds higher
         // shifts, so it wins ties against what the earlier chunks left in `best` (prev)
@@ -566,35 +575,37 @@ k_bitslice(BitsliceArgs a)
             const int web = 32 * wg0 + idx + 1;
             bool st = store_ok;
             if (MULTI && chunk != 0) st = st && best >= prev;
-            store_if(a.h.best + oidx, best, st);
-            store_if(a.h.web + oidx, web, st);
-            oidx += g.W;
+            store_if<0>(lane_best, orow, row_bytes, best, st);
+            store_if<0>(lane_web, orow, row_bytes, web, st);
+            orow++;
         };
         // what the earlier chunks left in `best` for the next output row + k (only read where it is stored)
         auto load_prev = [&](int k) {
             int v = 0;
-            if (MULTI && chunk != 0 && store_ok) v = a.h.best[oidx + k * g.W];
+            if (MULTI && chunk != 0 && store_ok) v = lane_best[(size_t)(orow + k) * g.W];
             return v;
         };
         // C2: the two pixels of a lane (columns ximg and ximg + 32) of one finished row
         auto put2 = [&](int best0, int idx0, int best1, int idx1) {
-            store_if(a.h.best + oidx, best0, store_ok);
-            store_if(a.h.web + oidx, idx0 + 1, store_ok);
-            store_if(a.h.best + oidx + TW, best1, store_ok2);
-            store_if(a.h.web + oidx + TW, idx1 + 1, store_ok2);
-            oidx += g.W;
+            store_if<0>(lane_best, orow, row_bytes, best0, store_ok);
+            store_if<0>(lane_web, orow, row_bytes, idx0 + 1, store_ok);
+            store_if<TW>(lane_best, orow, row_bytes, best1, store_ok2);
+            store_if<TW>(lane_web, orow, row_bytes, idx1 + 1, store_ok2);
+            orow++;
         };
         // HP: the 2 * NW pixels of a lane of one finished row: word w covers columns ximg + w * WCOLS and that + 16
         auto put_hp = [&](const int *bl, const int *il, const int *bh, const int *ih) {
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-                const int xo = w * WCOLS;
-                store_if(a.h.best + oidx + xo, bl[w], ximg + xo < g.W);
-                store_if(a.h.web + oidx + xo, il[w] + 1, ximg + xo < g.W);
-                store_if(a.h.best + oidx + xo + 16, bh[w], ximg + xo + 16 < g.W);
-                store_if(a.h.web + oidx + xo + 16, ih[w] - 16 + 1, ximg + xo + 16 < g.W);
+            store_if<0>(lane_best, orow, row_bytes, bl[0], ximg < g.W);
+            store_if<0>(lane_web, orow, row_bytes, il[0] + 1, ximg < g.W);
+            store_if<16>(lane_best, orow, row_bytes, bh[0], ximg + 16 < g.W);
+            store_if<16>(lane_web, orow, row_bytes, ih[0] - 16 + 1, ximg + 16 < g.W);
+            if constexpr (NW == 2) {
+                store_if<WCOLS>(lane_best, orow, row_bytes, bl[NW - 1], ximg + WCOLS < g.W);
+                store_if<WCOLS>(lane_web, orow, row_bytes, il[NW - 1] + 1, ximg + WCOLS < g.W);
+                store_if<WCOLS + 16>(lane_best, orow, row_bytes, bh[NW - 1], ximg + WCOLS + 16 < g.W);
+                store_if<WCOLS + 16>(lane_web, orow, row_bytes, ih[NW - 1] - 16 + 1, ximg + WCOLS + 16 < g.W);
             }
-            oidx += g.W;
+            orow++;
         };
         // winner-take-all of G rows held as Vs[G][NW][PV] / Ms[G][NW], then the stores: one WTA over both words
         // of a pixel, or (C2) one per word, the 2*G single-word chains interleaved like rows, or (HP) one per
@@ -650,23 +661,8 @@ k_bitslice(BitsliceArgs a)
         // ring row of x = tslot + r, tslot < N, r < RB
         auto wrap_t = [&](int x) { return N >= RB ? wrap_hi(x, N) : x % N; };
 
-        // Blocks of RB padded rows.  The 2*HALF rows that only fill the window come first: a short block of
-        // (2*HALF) % RB rows, then whole blocks that add and never subtract or output (`filling`), so that every
-        // block from the first output row on is a whole, branch-free `steady` block (but the run's ragged end).
-        constexpr int FILL0 = (2 * HALF) % RB;
-        int nrows = 0;
-        for (int p0 = ja; p0 < last_pr; p0 += nrows) {
-            nrows = min((FILL0 != 0 && p0 == ja) ? FILL0 : RB, last_pr - p0);
-            const bool steady = p0 >= first_out && nrows == RB;
-            const bool filling = p0 + nrows <= first_out;
-
-            // MULTI: the earlier chunks' `best` of the rows this block finishes, asked for now so that the loads
-            // are back long before the stores that depend on them (they used to be one exposed L2 round trip per row)
-            int prev[RB];
-#pragma unroll
-            for (int r = 0; r < RB; r++) prev[r] = steady ? load_prev(r) : 0;
-
-            // ---------------- pass A: 32 walkers ----------------
+        // ---------------- pass A: 32 walkers over the nrows rows of the block at padded row p0 ----------------
+        auto pass_a = [&](int p0, int nrows) {
             {
                 const bool active = wr < nrows;
                 const int slot = wr;
@@ -690,9 +686,58 @@ k_bitslice(BitsliceArgs a)
                 }
             }
             __syncwarp();
-
             // prefetch the next block's walker inputs; they land while pass B runs
             if (p0 + nrows + wr < last_pr) load_walk_raw(in, a.h, p0 + nrows + wr, rbit, lbit);
+        };
+        // rows that only fill the window: they enter the ring and the sums, nothing leaves, nothing is stored
+        auto fill_rows = [&](int nrows) {
+#pragma unroll 1
+            for (int r = 0; r < nrows; r++) {
+                uint32_t hn[NW][5], en[EC];
+#pragma unroll
+                for (int w = 0; w < NW; w++) load_h(r, w, hn[w]);
+                to_cols(hn, en);
+                tm_store<EC>(tring + wrap_t(tslot + r) * EC, en);
+#pragma unroll
+                for (int w = 0; w < NW; w++) planes_add<PV, KH>(V[w], hn[w]);
+            }
+        };
+        auto advance = [&](int nrows) {
+            __syncwarp();
+            mslot0 += nrows;
+            mslot0 = mslot0 >= NRM ? mslot0 - NRM : mslot0;
+            // (no remainder by N here: a conditional subtraction stays on the uniform datapath, and with it the ring
+            // rows of the next block's loads and stores)
+            tslot += nrows;
+            if (N >= RB) {
+                tslot = tslot >= N ? tslot - N : tslot;
+            } else {
+                tslot %= N;
+            }
+        };
+
+        // Blocks of RB padded rows.  The 2*HALF rows that only fill the window come first: a short block of
+        // (2*HALF) % RB rows (this prologue), then whole blocks that add and never subtract or output (`filling`),
+        // so that every block from the first output row on is a whole, branch-free `steady` block (but the run's
+        // ragged end).  A run always has more than 2*HALF padded rows, so the short block is never cut.
+        constexpr int FILL0 = (2 * HALF) % RB;
+        if constexpr (FILL0 != 0) {
+            pass_a(ja, FILL0);
+            fill_rows(FILL0);
+            advance(FILL0);
+        }
+        for (int p0 = ja + FILL0; p0 < last_pr; p0 += RB) {
+            const int nrows = min(RB, last_pr - p0);
+            const bool steady = p0 >= first_out && nrows == RB;
+            const bool filling = p0 + RB <= first_out;
+
+            // MULTI: the earlier chunks' `best` of the rows this block finishes, asked for now so that the loads
+            // are back long before the stores that depend on them (they used to be one exposed L2 round trip per row)
+            int prev[RB];
+#pragma unroll
+            for (int r = 0; r < RB; r++) prev[r] = steady ? load_prev(r) : 0;
+
+            pass_a(p0, nrows);
 
             // ---------------- pass B: 32 pixel columns ----------------
             if (steady) {
@@ -743,30 +788,7 @@ k_bitslice(BitsliceArgs a)
                     finish_rows(std::integral_constant<int, G>{}, Vs, Ms, prev + r);
                 }
             } else if (filling) {
-                // the window is still filling and no row of this block completes an output row: the rows enter the
-                // ring and the sums, nothing leaves, nothing is stored
-                if (nrows == RB) {
-#pragma unroll
-                    for (int r = 0; r < RB; r++) {
-                        uint32_t hn[NW][5], en[EC];
-#pragma unroll
-                        for (int w = 0; w < NW; w++) load_h(r, w, hn[w]);
-                        to_cols(hn, en);
-                        tm_store<EC>(tring + wrap_t(tslot + r) * EC, en);
-#pragma unroll
-                        for (int w = 0; w < NW; w++) planes_add<PV, KH>(V[w], hn[w]);
-                    }
-                } else {
-                    for (int r = 0; r < nrows; r++) {
-                        uint32_t hn[NW][5], en[EC];
-#pragma unroll
-                        for (int w = 0; w < NW; w++) load_h(r, w, hn[w]);
-                        to_cols(hn, en);
-                        tm_store<EC>(tring + wrap_t(tslot + r) * EC, en);
-#pragma unroll
-                        for (int w = 0; w < NW; w++) planes_add<PV, KH>(V[w], hn[w]);
-                    }
-                }
+                fill_rows(RB);
             } else {
                 // the ragged last block of a run
                 for (int r = 0; r < nrows; r++) {
@@ -805,10 +827,7 @@ k_bitslice(BitsliceArgs a)
                     }
                 }
             }
-            __syncwarp();
-            mslot0 += nrows;
-            mslot0 = mslot0 >= NRM ? mslot0 - NRM : mslot0;
-            tslot = (tslot + nrows) % N;
+            advance(nrows);
         }
     }
 
@@ -873,25 +892,33 @@ int launch_one(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
     if (h.force_segs > 0) {
         segs = h.force_segs;  // development hook (sm_set_option)
     } else if (h.npairs == 1) {
-        // latency mode (one pair per launch).  All CTAs do the same work: a run of R rows costs R + 2*half
-        // window-filling rows (about half a row each) + a fixed start-up.  The kernel is bound by the ALU pipe, so an SM takes as long as
-        // the work of the CTAs that land on it (they are dealt round-robin: ceil(CTAs / SMs) on the fullest),
-        // stretched when too few warps are resident to keep the pipe busy (measured: about 55 % of the pipe
-        // with 4 warps per SM, 93 % with 8, flat from 12).  Pick the number of runs that minimises that
-        // (short runs pay more filling rows, long runs leave SMs idle or thin); a cost model instead of
-        // timing candidates at sm_create.
+        // latency mode (one pair per launch).  All CTAs do the same work: a run of R rows costs R rows, the
+        // window-filling blocks in front of them (whole blocks of RB rows, about half a row's work per row: pass A and
+        // one add, no subtraction, no winner-take-all) and a fixed start-up.  The kernel is bound by the ALU pipe, so
+        // an SM takes as long as the work of the CTAs that land on it: ceil(CTAs / SMs) on the fullest while the grid
+        // is under about 1.7 waves of CTA slots (everything resident at once or a ragged second round), CTAs / SMs
+        // once the block scheduler has several rounds to even things out.  Too few resident warps leave the pipe
+        // idle (measured on one-pair launches, tools/sweep_runs.py: 4 warps per SM reach about 0.6 of the rate of
+        // 16, 8 about 0.85, 12 about 0.94).  Pick the number of runs that minimises that: a cost model, nothing
+        // is timed at sm_create.
         const int start_rows = 4;
-        const double fill_weight = 0.5;  // a window-filling row: pass A and one add, no subtraction, no winner-take-all
+        const int fill_rows = (2 * HALF + C::RB - 1) / C::RB * C::RB;
+        auto eff_of = [](int warps) {
+            if (warps >= 16) return 1.0;
+            if (warps >= 12) return 0.94 + (warps - 12) * (0.06 / 4);
+            if (warps >= 8) return 0.85 + (warps - 8) * (0.09 / 4);
+            return 0.6 + (warps > 4 ? warps - 4 : 0) * (0.25 / 4);
+        };
         double best_cost = -1.0;
         segs = 1;
         for (int sg = 1; sg <= max_segs; sg++) {
             int rows, got = shape(sg, rows);
             if (got != sg) continue;
             const int ctas = ctas_per_run * got;
-            const int per_sm = (ctas + num_sms - 1) / num_sms;
-            const int resident = (per_sm < C::CTAS_PER_SM ? per_sm : C::CTAS_PER_SM) * C::WPC;
-            const double eff = resident >= 12 ? 1.0 : (resident <= 4 ? 0.55 : 0.55 + 0.45 * (resident - 4) / 8.0);
-            const double cost = per_sm * (rows + fill_weight * 2 * HALF + start_rows) / eff;
+            const int per_sm_max = (ctas + num_sms - 1) / num_sms;
+            const double per_sm = 10 * ctas < 17 * slots ? (double)per_sm_max : (double)ctas / num_sms + 0.05;
+            const int resident = (per_sm_max < C::CTAS_PER_SM ? per_sm_max : C::CTAS_PER_SM) * C::WPC;
+            const double cost = per_sm * (rows + 0.5 * fill_rows + start_rows) / eff_of(resident);
             if (best_cost < 0 || cost < best_cost) best_cost = cost, segs = got;
             if (ctas > 6 * slots) break;
         }

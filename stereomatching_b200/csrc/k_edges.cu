@@ -289,13 +289,22 @@ __device__ __forceinline__ uint32_t edge_nibble(const int (&p)[3][6], F &&edge)
     return e;
 }
 
-__device__ __forceinline__ void unpack_row(const uint8_t *__restrict__ row, int x4, int (&p)[6])
+// pixels x4-1 .. x4+4 of a row as three aligned words (x4 a multiple of 4, 4 <= x4 <= W - 8)
+struct RowWords {
+    uint32_t a, b, c;
+};
+
+__device__ __forceinline__ RowWords load_row(const uint8_t *__restrict__ row, int x4)
 {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(row + x4);
-    const uint32_t a = __ldg(w - 1), b = __ldg(w), c = __ldg(w + 1);
-    p[0] = a >> 24;
-    p[1] = b & 255, p[2] = (b >> 8) & 255, p[3] = (b >> 16) & 255, p[4] = b >> 24;
-    p[5] = c & 255;
+    return RowWords{__ldg(w - 1), __ldg(w), __ldg(w + 1)};
+}
+
+__device__ __forceinline__ void unpack_row(const RowWords &r, int (&p)[6])
+{
+    p[0] = r.a >> 24;
+    p[1] = r.b & 255, p[2] = (r.b >> 8) & 255, p[3] = (r.b >> 16) & 255, p[4] = r.b >> 24;
+    p[5] = r.c & 255;
 }
 
 template <int VARIANT, bool WRITE_U8>
@@ -351,10 +360,20 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
 
     int p[3][6];       // rows y-1, y, y+1 of the sliding window (xfast threads only)
     int have_y = -2;   // p[1], p[2] hold rows have_y, have_y + 1 (unwrapped successor) when have_y >= 0
+    RowWords ahead = {0u, 0u, 0u};  // the row the NEXT step will need, asked for one step early
+    int ahead_y = -2;
+    bool rowvalid;
+    int y = frame_row(pr0, rowvalid);
     for (int pr = pr0; pr < pr1; pr++) {
-        bool rowvalid;
-        const int y = frame_row(pr, rowvalid);
         uint32_t e = 0, v = 0;
+        // frame row of the next padded row: one step further (mod FH for WRAP), no division in the loop
+        int yn = y + 1;
+        bool nvalid = true;
+        if (VARIANT == SM_WRAP) {
+            yn = yn >= FH ? yn - FH : yn;
+        } else {
+            nvalid = yn >= 0 && yn < FH;
+        }
         if (wd < g.WPR && rowvalid) {
             int ym = y - 1, yp = y + 1;
             if (VARIANT == SM_WRAP) {
@@ -363,15 +382,31 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
             }
             if (xfast && ym >= 0 && yp < FH) {
                 // consecutive padded rows are consecutive frame rows (mod FH): the window slides, one new row
-                // of three words per step
+                // of three words per step, and that row was asked for during the previous step
+                RowWords top;
+                if (ahead_y == yp) {
+                    top = ahead;
+                } else {
+                    top = load_row(img + (size_t)yp * W, xs);
+                }
                 if (have_y == ym) {
 #pragma unroll
                     for (int k = 0; k < 6; k++) p[0][k] = p[1][k], p[1][k] = p[2][k];
                 } else {
-                    unpack_row(img + (size_t)ym * W, xs, p[0]);
-                    unpack_row(img + (size_t)y * W, xs, p[1]);
+                    unpack_row(load_row(img + (size_t)ym * W, xs), p[0]);
+                    unpack_row(load_row(img + (size_t)y * W, xs), p[1]);
                 }
-                unpack_row(img + (size_t)yp * W, xs, p[2]);
+                {
+                    // the row below the next step's row (its `yp`), if that step slides on from this one
+                    int y2 = yn + 1;
+                    if (VARIANT == SM_WRAP) y2 = y2 >= FH ? y2 - FH : y2;
+                    ahead_y = -2;
+                    if (pr + 1 < pr1 && nvalid && yn == yp && y2 < FH) {
+                        ahead = load_row(img + (size_t)y2 * W, xs);
+                        ahead_y = y2;
+                    }
+                }
+                unpack_row(top, p[2]);
                 have_y = y;
                 e = thresholds_exact ? edge_nibble(p, edge_hi) : edge_nibble(p, edge_lut);
                 v = 0xFu;
@@ -421,6 +456,13 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
                         else
                             b = edge_lut(tl + ml + bl, tr + mr + br) | edge_lut(tl + tc + tr, bl + bc + br) |
                                 edge_lut(tl + tc + ml, mr + bc + br) | edge_lut(bl + bc + ml, tc + tr + mr);
+                    } else if (W >= 2 && FH >= 2) {
+                        // A stencil that touches the ghost area always fires: on the side towards the border one
+                        // detector sees three 128.0 cells (l = 128 exactly) or, in a corner, one (r > 42) against
+                        // image cells below 1 on the other side, a difference of more than 1, and the limit is
+                        // clamped to at most 1 (stereo-ghost.c: CLAMP, util.h:24-26).  Only one-pixel-wide or
+                        // one-pixel-high frames have ghost cells on BOTH sides of a detector.
+                        b = 1;
                     } else {
                         auto B = [&](int dx, int dy) {
                             const int q = p[dy + 1][k + 1 + dx];
@@ -465,6 +507,8 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
                 RB[o] = ew & vw;
             }
         }
+        y = yn;
+        rowvalid = nvalid;
     }
 }
 
