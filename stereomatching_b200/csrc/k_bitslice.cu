@@ -655,8 +655,8 @@ k_bitslice(BitsliceArgs a)
 #pragma unroll
             for (int w = 0; w < NW; w++) M[w] = Mq[mslot_c * MROW + lane * NW + w];
         };
-        // ring index helpers: x in [0, 2n) -> x mod n, and x in [-n, n) -> x mod n, as one add + one unsigned min
-        auto wrap_hi = [](int x, int n) { return (int)min((unsigned)x, (unsigned)(x - n)); };
+        // ring index helpers: x in [0, 2n) -> x mod n, and x in [-n, n) -> x mod n
+        auto wrap_hi = [](int x, int n) { return x >= n ? x - n : x; };
         auto wrap_m = [&](int ms) { return ms < 0 ? ms + NRM : (ms >= NRM ? ms - NRM : ms); };
         // ring row of x = tslot + r, tslot < N, r < RB
         auto wrap_t = [&](int x) { return N >= RB ? wrap_hi(x, N) : x % N; };

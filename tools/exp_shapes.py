@@ -31,6 +31,9 @@ POINTS = {
     "w5": (1920, 1080, 64, 5),
     "w1": (1920, 1080, 30, 1),
     "c2d32": (1920, 1080, 32, 9),
+    "c2d16": (1920, 1080, 16, 9),
+    "d16w21": (1920, 1080, 16, 21),
+    "small": (240, 135, 30, 21),
 }
 SHAPES = [{}]
 EXTRA = [{"SMB_TR": "16"}, {"SMB_TR": "64"}]
