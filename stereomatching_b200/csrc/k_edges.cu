@@ -105,7 +105,7 @@ template int launch_edges<double>(const double *, int, int, int, int, int, doubl
 // sums L, R in [0, 765] (each brightness is k/256 exactly, so the two additions are exact
 // and ((a+b)+c)/3.0 == fl((L/256)/3)) and on the threshold.  k_edge_lut evaluates the
 // reference's FP64 expression (stereo.c:16-28) once for all 766 x 766 pairs into a bit
-// table; k_edges_lut then needs integer adds and four table bits per pixel.  Pixels whose
+// table; the detector then needs integer adds and four table decisions per pixel.  Pixels whose
 // 3x3 stencil leaves the image in the GHOST variant see the 128.0 ghost cells
 // (stereo-ghost.c:384-385), which are not 8-bit values: they take the FP64 path.
 constexpr int LUT_N = 766, LUT_WORDS = 24;  // 766 bits per row -> 24 words
@@ -168,107 +168,15 @@ __global__ void __launch_bounds__(256) k_edge_thresholds(uint32_t *__restrict__ 
     if (!ok) atomicAnd(lut + LUT_FLAG, 0u);
 }
 
-// one pixel, any position: wraps (WRAP) or falls back to FP64 with the 128.0 ghost cells (GHOST border)
-template <int VARIANT>
-__device__ __forceinline__ int edge_pixel(const uint8_t *__restrict__ img, int W, int FH, int x, int y, double thr,
-                                          const uint32_t *__restrict__ lut)
-{
-    int xm = x - 1, xp = x + 1, ym = y - 1, yp = y + 1;
-    if (VARIANT == SM_WRAP) {
-        xm = xm < 0 ? xm + W : xm;
-        xp = xp >= W ? xp - W : xp;
-        ym = ym < 0 ? ym + FH : ym;
-        yp = yp >= FH ? yp - FH : yp;
-    } else if (xm < 0 || xp >= W || ym < 0 || yp >= FH) {
-        double b[3][3];
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-                int xx = x + dx, yy = y + dy;
-                bool in = xx >= 0 && xx < W && yy >= 0 && yy < FH;
-                b[dy + 1][dx + 1] = in ? to_bright<uint8_t>(img[(size_t)yy * W + xx]) : 128.0;
-            }
-#define B(dx, dy) b[(dy) + 1][(dx) + 1]
-        return detect(B(-1, -1), B(-1, 0), B(-1, 1), B(1, -1), B(1, 0), B(1, 1), thr) |
-               detect(B(-1, -1), B(0, -1), B(1, -1), B(-1, 1), B(0, 1), B(1, 1), thr) |
-               detect(B(-1, -1), B(0, -1), B(-1, 0), B(1, 0), B(0, 1), B(1, 1), thr) |
-               detect(B(-1, 1), B(0, 1), B(-1, 0), B(0, -1), B(1, -1), B(1, 0), thr);
-#undef B
-    }
-    const uint8_t *r0 = img + (size_t)ym * W, *r1 = img + (size_t)y * W, *r2 = img + (size_t)yp * W;
-    const int tl = r0[xm], tc = r0[x], tr = r0[xp];
-    const int ml = r1[xm], mr = r1[xp];
-    const int bl = r2[xm], bc = r2[x], br = r2[xp];
-    return lut_bit(lut, tl + ml + bl, tr + mr + br)      // left_right       stereo.c:16-28
-           | lut_bit(lut, tl + tc + tr, bl + bc + br)    // top_bottom       stereo.c:30-42
-           | lut_bit(lut, tl + tc + ml, mr + bc + br)    // upleft_downright stereo.c:44-56
-           | lut_bit(lut, bl + bc + ml, tc + tr + mr);   // downleft_upright stereo.c:58-70
-}
-
-// Four consecutive pixels per thread: interior groups read three aligned words per image row
-// (9 loads instead of 32 byte loads) and store the four edge flags as one word.
-template <int VARIANT>
-__global__ void __launch_bounds__(256)
-k_edges_lut(const uint8_t *__restrict__ img, int W, int FH, int ystart, int nrows, double thr,
-            const uint32_t *__restrict__ lut, uint8_t *__restrict__ edges, size_t image_stride)
-{
-    // one image per grid z-slice (sm_run_batch detects a whole group of images in one launch)
-    img += blockIdx.z * image_stride;
-    edges += blockIdx.z * image_stride;
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int r = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x4 >= W || r >= nrows) return;
-    int y = ystart + r;
-    if (VARIANT == SM_WRAP) {
-        y %= FH;
-        if (y < 0) y += FH;
-    } else if (y < 0 || y >= FH) {
-        return;
-    }
-    int ym = y - 1, yp = y + 1;
-    if (VARIANT == SM_WRAP) {
-        ym = ym < 0 ? ym + FH : ym;
-        yp = yp >= FH ? yp - FH : yp;
-    }
-    const bool rows_in = ym >= 0 && yp < FH;
-    const bool fast = rows_in && (W & 3) == 0 && x4 >= 4 && x4 + 8 <= W &&
-                      ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(edges)) & 3) == 0;
-    if (!fast) {
-        for (int k = 0; k < 4 && x4 + k < W; k++)
-            edges[(size_t)y * W + x4 + k] = (uint8_t)edge_pixel<VARIANT>(img, W, FH, x4 + k, y, thr, lut);
-        return;
-    }
-    int p[3][6];  // pixels x4-1 .. x4+4 of the three rows
-    const int ys[3] = {ym, y, yp};
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(img + (size_t)ys[j] * W + x4);
-        const uint32_t a = __ldg(w - 1), b = __ldg(w), c = __ldg(w + 1);
-        p[j][0] = a >> 24;
-        p[j][1] = b & 255, p[j][2] = (b >> 8) & 255, p[j][3] = (b >> 16) & 255, p[j][4] = b >> 24;
-        p[j][5] = c & 255;
-    }
-    uint32_t out = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int tl = p[0][k], tc = p[0][k + 1], tr = p[0][k + 2];
-        const int ml = p[1][k], mr = p[1][k + 2];
-        const int bl = p[2][k], bc = p[2][k + 1], br = p[2][k + 2];
-        const int e = lut_bit(lut, tl + ml + bl, tr + mr + br) | lut_bit(lut, tl + tc + tr, bl + bc + br) |
-                      lut_bit(lut, tl + tc + ml, mr + bc + br) | lut_bit(lut, bl + bc + ml, tc + tr + mr);
-        out |= (uint32_t)e << (8 * k);
-    }
-    *reinterpret_cast<uint32_t *>(edges + (size_t)y * W + x4) = out;
-}
-
 // ---- edges straight into the packed planes ---------------------------------------------------
 // The whole-algorithm and batch paths never need the byte edge maps: this kernel detects the edges of BOTH
 // images of a pair over the PADDED band (rows [row0-half, row1+half), columns [-PADL, WPR*32-PADL)) and writes
 // the three 1-bit planes LA / LB / RB of sm_common.cuh directly, with the border policy of the variant applied
 // to the coordinates (a padding pixel of the WRAP variant IS the wrapped image pixel; GHOST padding is zero and
-// invalid).  It stands in for k_edges_lut + k_pack: one launch and 4 B per pixel of traffic less.  Thread =
-// 4 consecutive pixels of one image; eight threads' nibbles are OR-reduced into a 32-pixel word by shuffles.
+// invalid).  It stands in for a byte-map detector followed by k_pack: one launch and 4 B per pixel of traffic
+// less.  Thread = 4 consecutive pixels of one image over EP_ROWS rows, a sliding window of three rows (three aligned
+// words per new row, asked for one step early); eight threads' nibbles are OR-reduced into a 32-pixel word by
+// shuffles.
 // WRITE_U8: also store the byte maps (in-image pixels only), for sm_download(SM_EDGES*) and the debug planes.
 constexpr int EP_ROWS = 8;  // padded rows per block of k_edges_planes
 
@@ -543,19 +451,6 @@ int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s)
 
 size_t edge_lut_words() { return (size_t)LUT_FLAG + 1; }
 
-int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
-                     const uint32_t *lut, uint8_t *edges, cudaStream_t s, int n_images, size_t image_stride)
-{
-    dim3 block(64, 4);
-    dim3 grid(((W + 3) / 4 + block.x - 1) / block.x, (nrows + block.y - 1) / block.y, n_images);
-    if (variant == SM_WRAP)
-        k_edges_lut<SM_WRAP><<<grid, block, 0, s>>>(img, W, FH, ystart, nrows, threshold, lut, edges, image_stride);
-    else
-        k_edges_lut<SM_GHOST><<<grid, block, 0, s>>>(img, W, FH, ystart, nrows, threshold, lut, edges, image_stride);
-    SM_CUDA(cudaGetLastError());
-    return 1;
-}
-
 void warm_edges(int variant)
 {
     warm_kernel(k_edge_lut);
@@ -564,7 +459,6 @@ void warm_edges(int variant)
     if (variant == SM_WRAP) {
         warm_kernel(k_edges<uint8_t, SM_WRAP>);
         warm_kernel(k_edges<double, SM_WRAP>);
-        warm_kernel(k_edges_lut<SM_WRAP>);
         warm_kernel(k_edges_planes<SM_WRAP, true>);
         warm_kernel(k_edges_planes<SM_WRAP, false>);
     } else {
@@ -572,7 +466,6 @@ void warm_edges(int variant)
         warm_kernel(k_edges_planes<SM_GHOST, false>);
         warm_kernel(k_edges<uint8_t, SM_GHOST>);
         warm_kernel(k_edges<double, SM_GHOST>);
-        warm_kernel(k_edges_lut<SM_GHOST>);
     }
 }
 

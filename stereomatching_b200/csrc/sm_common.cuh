@@ -117,8 +117,6 @@ int launch_edges(const T *img, int W, int FH, int ystart, int nrows, int variant
 // integer fast path of the edge detector for 8-bit images: a 766 x 766 bit table per threshold
 int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s);
 size_t edge_lut_words();
-int launch_edges_lut(const uint8_t *img, int W, int FH, int ystart, int nrows, int variant, double threshold,
-                     const uint32_t *lut, uint8_t *edges, cudaStream_t s, int n_images = 1, size_t image_stride = 0);
 
 // both images of npairs pairs -> packed planes in one launch (edges1/edges2 non-NULL: the byte maps as well)
 int launch_edges_planes(const uint8_t *img1, const uint8_t *img2, int FH, int row0, int variant, const PackedGeom &g,
