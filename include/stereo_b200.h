@@ -112,8 +112,8 @@ int sm_host_free(void *ptr);
 /* Replaces the device allocations at the top of algorithm() (stereo.cu:299-306;
  * stereo-ghost.cu:299-307) and allocate_matches/allocate_scores (stereo.cu:100-106,
  * 159-165).  num_shifts is the reference's compile-time NUM_SHIFTS (stereo.cu:6),
- * here a run-time value in [1, 512]; square_width in [1, 63] (the window is
- * (2*(square_width/2)+1)^2, stereo.cu:144-146) and <= width, height
+ * here a run-time value in [1, 512]; square_width in [0, 63] (the window is
+ * (2*(square_width/2)+1)^2, stereo.cu:144-146: 0 is the 1x1 window, as in the reference) and <= width, height
  * (stereo.cu:395-398). */
 int sm_create(sm_ctx **ctx, int device, int width, int height, int num_shifts,
               int square_width, int variant);

@@ -287,7 +287,8 @@ void profile_free(sm_ctx *c)
 
 extern "C" const char *sm_last_error(void) { return g_err; }
 
-extern "C" int sm_version(void) { return (1 << 16) | 1; }  // 1.1: sm_measure_copy_peak, sm_multi_*, sm_bands_*
+// 1.1: sm_multi_*, sm_bands_*; 1.2: sm_set_option / sm_get_info, square_width 0, the microbenchmarks moved out
+extern "C" int sm_version(void) { return (1 << 16) | 2; }
 
 extern "C" int sm_device_count(void)
 {
