@@ -178,7 +178,12 @@ __global__ void __launch_bounds__(256) k_edge_thresholds(uint32_t *__restrict__ 
 // words per new row, asked for one step early); eight threads' nibbles are OR-reduced into a 32-pixel word by
 // shuffles.
 // WRITE_U8: also store the byte maps (in-image pixels only), for sm_download(SM_EDGES*) and the debug planes.
-constexpr int EP_ROWS = 8;  // padded rows per block of k_edges_planes
+// Padded rows per block and resident blocks per SM of k_edges_planes.  Measured on the fixtures, wrap / ghost
+// (tools/edges_time.py): 8 rows and 56 registers (9 blocks per SM: a 1080p pair is 1.04 waves) 28.4 / 31.8 us at 1080p,
+// 12.3 / 14.4 us at 480x270; 4 rows and 48 registers (10 blocks per SM, one wave) 24.6 / 30.4 and 8.2 / 12.3 us, 4K
+// unchanged (63 / 75 us); 2 rows or fewer lose the sliding window at 4K, 12 blocks per SM spill.
+constexpr int EP_ROWS = 4;
+constexpr int EP_BLOCKS_PER_SM = 10;
 
 // detector decisions of 4 consecutive pixels from their 3 x 6 neighbourhood p[row][x4-1 .. x4+4]
 template <typename F>
@@ -202,10 +207,18 @@ struct RowWords {
     uint32_t a, b, c;
 };
 
-__device__ __forceinline__ RowWords load_row(const uint8_t *__restrict__ row, int x4)
+// WRAP threads on the word path are interior (4 <= x4 <= W - 8: the seam takes the gather).  GHOST threads may sit at
+// the frame's border: there is nothing beside the frame, and the pixel next to the border is decided without it.
+template <int VARIANT>
+__device__ __forceinline__ RowWords load_row(const uint8_t *__restrict__ row, int x4, int W)
 {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(row + x4);
-    return RowWords{__ldg(w - 1), __ldg(w), __ldg(w + 1)};
+    if (VARIANT == SM_WRAP) return RowWords{__ldg(w - 1), __ldg(w), __ldg(w + 1)};
+    RowWords r;
+    r.b = __ldg(w);
+    r.a = x4 >= 4 ? __ldg(w - 1) : 0u;
+    r.c = x4 + 8 <= W ? __ldg(w + 1) : 0u;
+    return r;
 }
 
 __device__ __forceinline__ void unpack_row(const RowWords &r, int (&p)[6])
@@ -215,8 +228,60 @@ __device__ __forceinline__ void unpack_row(const RowWords &r, int (&p)[6])
     p[5] = r.c & 255;
 }
 
+// GHOST's rare path: widths that are no multiple of 4, unaligned images, frames of one row (its borders are on the
+// word path).  The 3 x 6 neighbourhood of the thread's four pixels byte by byte, every load independent, the cells
+// outside the frame marked -1; then per pixel the integer detector where its stencil is inside, else the border
+// rule or -- one-pixel-wide / one-pixel-high frames -- the FP64 detector with the 128.0 ghost cells
+// (stereo-ghost.c:384-385).  A real call, so that the FP64 fallback does not cost the word path its registers.
+__device__ __noinline__ void edge_gather_ghost(const uint8_t *__restrict__ img, int W, int FH, int x4, int ym, int y, int yp,
+                                               double thr, const uint32_t *__restrict__ lut, const uint16_t *hi_s,
+                                               bool thresholds_exact, uint32_t &e, uint32_t &v)
+{
+    auto edge = [&](int L, int R) {
+        return thresholds_exact ? (int)(max(L, R) > (int)hi_s[min(L, R)]) : lut_bit(lut, L, R);
+    };
+    int p[3][6];
+    const int ys[3] = {ym, y, yp};
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int x = x4 - 1 + k;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const bool in = x >= 0 && x < W && ys[j] >= 0 && ys[j] < FH;
+            p[j][k] = in ? (int)__ldg(img + (size_t)ys[j] * W + x) : -1;
+        }
+    }
+    e = v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = x4 + k;
+        if (x < 0 || x >= W) continue;  // ghost padding: zero and invalid
+        int b;
+        if ((p[0][k] | p[0][k + 1] | p[0][k + 2] | p[1][k] | p[1][k + 2] | p[2][k] | p[2][k + 1] | p[2][k + 2]) >= 0) {
+            const int tl = p[0][k], tc = p[0][k + 1], tr = p[0][k + 2];
+            const int ml = p[1][k], mr = p[1][k + 2];
+            const int bl = p[2][k], bc = p[2][k + 1], br = p[2][k + 2];
+            b = edge(tl + ml + bl, tr + mr + br) | edge(tl + tc + tr, bl + bc + br) | edge(tl + tc + ml, mr + bc + br) |
+                edge(bl + bc + ml, tc + tr + mr);
+        } else if (W >= 2 && FH >= 2) {
+            b = 1;  // the border rule (k_edges_planes)
+        } else {
+            auto B = [&](int dx, int dy) {
+                const int q = p[dy + 1][k + 1 + dx];
+                return q < 0 ? 128.0 : to_bright<uint8_t>((uint8_t)q);
+            };
+            b = detect(B(-1, -1), B(-1, 0), B(-1, 1), B(1, -1), B(1, 0), B(1, 1), thr) |
+                detect(B(-1, -1), B(0, -1), B(1, -1), B(-1, 1), B(0, 1), B(1, 1), thr) |
+                detect(B(-1, -1), B(0, -1), B(-1, 0), B(1, 0), B(0, 1), B(1, 1), thr) |
+                detect(B(-1, 1), B(0, 1), B(-1, 0), B(0, -1), B(1, -1), B(1, 0), thr);
+        }
+        e |= (uint32_t)b << k;
+        v |= 1u << k;
+    }
+}
+
 template <int VARIANT, bool WRITE_U8>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, EP_BLOCKS_PER_SM)
 k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img2, int FH, int row0, PackedGeom g,
                double thr, const uint32_t *__restrict__ lut, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB,
                uint32_t *__restrict__ RB, uint8_t *__restrict__ edges1, uint8_t *__restrict__ edges2, size_t image_stride,
@@ -243,15 +308,19 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
     const int x4 = t * 4 - PADL;
     const int pr0 = blockIdx.y * EP_ROWS, pr1 = min(g.ER, pr0 + EP_ROWS);
     // WRAP: a padding pixel IS the wrapped image pixel, so the thread works at its wrapped column xs (when the
-    // width is a multiple of 4 its four pixels stay contiguous there).  Word path: the four pixels and their
-    // neighbours are inside the image and word-aligned; otherwise the 3 x 6 neighbourhood is gathered byte by byte
-    // through the wrap (WRAP) or the pixels are taken one by one (GHOST borders: FP64 with the 128.0 ghost cells).
+    // width is a multiple of 4 its four pixels stay contiguous there).  Word path (widths that are a multiple of 4,
+    // word-aligned images): WRAP, the four pixels and their neighbours are inside the image (the seam is gathered
+    // through the wrap); GHOST, the four pixels are inside a frame of at least two rows, and a pixel whose stencil
+    // touches the ghost area is an edge without any arithmetic (below).  Everything else is gathered byte by byte.
     int xs = x4;
     if (VARIANT == SM_WRAP) {
         xs %= W;
         if (xs < 0) xs += W;
     }
-    const bool xfast = wd < g.WPR && (W & 3) == 0 && xs >= 4 && xs + 8 <= W && (reinterpret_cast<uintptr_t>(img) & 3) == 0;
+    const bool xfast = wd < g.WPR && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0 &&
+                       (VARIANT == SM_WRAP ? xs >= 4 && xs + 8 <= W : FH >= 2 && xs >= 0 && xs + 4 <= W);
+    // GHOST: this thread's pixels at the frame's left / right border
+    const uint32_t xborder = VARIANT == SM_GHOST ? (xs == 0 ? 1u : 0u) | (xs + 4 == W ? 8u : 0u) : 0u;
     auto frame_row = [&](int pr, bool &valid) {
         int y = row0 - g.half + pr;
         valid = true;
@@ -288,21 +357,26 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
                 ym = ym < 0 ? ym + FH : ym;
                 yp = yp >= FH ? yp - FH : yp;
             }
-            if (xfast && ym >= 0 && yp < FH) {
+            if (VARIANT == SM_GHOST && xfast && (ym < 0 || yp >= FH)) {
+                // GHOST, first or last row of the frame: every stencil touches the ghost area and fires (see the
+                // border rule below); nothing to load
+                have_y = -2;
+                e = v = 0xFu;
+            } else if (xfast && ym >= 0 && yp < FH) {
                 // consecutive padded rows are consecutive frame rows (mod FH): the window slides, one new row
                 // of three words per step, and that row was asked for during the previous step
                 RowWords top;
                 if (ahead_y == yp) {
                     top = ahead;
                 } else {
-                    top = load_row(img + (size_t)yp * W, xs);
+                    top = load_row<VARIANT>(img + (size_t)yp * W, xs, W);
                 }
                 if (have_y == ym) {
 #pragma unroll
                     for (int k = 0; k < 6; k++) p[0][k] = p[1][k], p[1][k] = p[2][k];
                 } else {
-                    unpack_row(load_row(img + (size_t)ym * W, xs), p[0]);
-                    unpack_row(load_row(img + (size_t)y * W, xs), p[1]);
+                    unpack_row(load_row<VARIANT>(img + (size_t)ym * W, xs, W), p[0]);
+                    unpack_row(load_row<VARIANT>(img + (size_t)y * W, xs, W), p[1]);
                 }
                 {
                     // the row below the next step's row (its `yp`), if that step slides on from this one
@@ -310,79 +384,40 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
                     if (VARIANT == SM_WRAP) y2 = y2 >= FH ? y2 - FH : y2;
                     ahead_y = -2;
                     if (pr + 1 < pr1 && nvalid && yn == yp && y2 < FH) {
-                        ahead = load_row(img + (size_t)y2 * W, xs);
+                        ahead = load_row<VARIANT>(img + (size_t)y2 * W, xs, W);
                         ahead_y = y2;
                     }
                 }
                 unpack_row(top, p[2]);
                 have_y = y;
                 e = thresholds_exact ? edge_nibble(p, edge_hi) : edge_nibble(p, edge_lut);
-                v = 0xFu;
-            } else if (VARIANT == SM_WRAP) {
-                // at the seam, or a width that is no multiple of 4: every byte through the wrap, all 18 loads
-                // independent (one memory round trip per row, not one per pixel)
-                int xk[6];
-#pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    int x = (x4 - 1 + k) % W;
-                    xk[k] = x < 0 ? x + W : x;
-                }
-                const int ys[3] = {ym, y, yp};
-#pragma unroll
-                for (int j = 0; j < 3; j++)
-#pragma unroll
-                    for (int k = 0; k < 6; k++) p[j][k] = __ldg(img + (size_t)ys[j] * W + xk[k]);
-                have_y = -2;
-                e = thresholds_exact ? edge_nibble(p, edge_hi) : edge_nibble(p, edge_lut);
+                // GHOST border rule: a stencil that touches the ghost area always fires.  Towards the border one
+                // detector sees three 128.0 cells (l = 128 exactly) or, in a corner, one (r > 42) against image cells
+                // below 1 on the other side: a difference above 41, and the limit is clamped to at most 1
+                // (stereo-ghost.c: CLAMP, util.h:24-26).  It needs frames of at least 2 x 2: a one-pixel-wide or
+                // one-pixel-high frame has ghost cells on BOTH sides of a detector (those take the gather path).
+                e |= xborder;
                 v = 0xFu;
             } else {
-                // GHOST, at the frame's border: gather the neighbourhood once (-1 = outside the frame, all loads
-                // independent), then per pixel the integer detector where its 3 x 3 stencil is inside and the FP64
-                // one with the 128.0 ghost cells (stereo-ghost.c:384-385) where it is not
                 have_y = -2;
-                const int ys[3] = {ym, y, yp};
-#pragma unroll
-                for (int j = 0; j < 3; j++)
+                if (VARIANT == SM_WRAP) {
+                    // at the seam of every row (and for widths that are no multiple of 4): every byte through the
+                    // wrap, all 18 loads independent (one memory round trip per row, not one per pixel)
+                    int xk[6];
 #pragma unroll
                     for (int k = 0; k < 6; k++) {
-                        const int x = x4 - 1 + k;
-                        const bool in = x >= 0 && x < W && ys[j] >= 0 && ys[j] < FH;
-                        p[j][k] = in ? (int)__ldg(img + (size_t)ys[j] * W + x) : -1;
+                        int x = (x4 - 1 + k) % W;
+                        xk[k] = x < 0 ? x + W : x;
                     }
+                    const int ys[3] = {ym, y, yp};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int x = x4 + k;
-                    if (x < 0 || x >= W) continue;
-                    int b;
-                    if ((p[0][k] | p[0][k + 1] | p[0][k + 2] | p[1][k] | p[1][k + 2] | p[2][k] | p[2][k + 1] | p[2][k + 2]) >= 0) {
-                        const int tl = p[0][k], tc = p[0][k + 1], tr = p[0][k + 2];
-                        const int ml = p[1][k], mr = p[1][k + 2];
-                        const int bl = p[2][k], bc = p[2][k + 1], br = p[2][k + 2];
-                        if (thresholds_exact)
-                            b = edge_hi(tl + ml + bl, tr + mr + br) | edge_hi(tl + tc + tr, bl + bc + br) |
-                                edge_hi(tl + tc + ml, mr + bc + br) | edge_hi(bl + bc + ml, tc + tr + mr);
-                        else
-                            b = edge_lut(tl + ml + bl, tr + mr + br) | edge_lut(tl + tc + tr, bl + bc + br) |
-                                edge_lut(tl + tc + ml, mr + bc + br) | edge_lut(bl + bc + ml, tc + tr + mr);
-                    } else if (W >= 2 && FH >= 2) {
-                        // A stencil that touches the ghost area always fires: on the side towards the border one
-                        // detector sees three 128.0 cells (l = 128 exactly) or, in a corner, one (r > 42) against
-                        // image cells below 1 on the other side, a difference of more than 1, and the limit is
-                        // clamped to at most 1 (stereo-ghost.c: CLAMP, util.h:24-26).  Only one-pixel-wide or
-                        // one-pixel-high frames have ghost cells on BOTH sides of a detector.
-                        b = 1;
-                    } else {
-                        auto B = [&](int dx, int dy) {
-                            const int q = p[dy + 1][k + 1 + dx];
-                            return q < 0 ? 128.0 : to_bright<uint8_t>((uint8_t)q);
-                        };
-                        b = detect(B(-1, -1), B(-1, 0), B(-1, 1), B(1, -1), B(1, 0), B(1, 1), thr) |
-                            detect(B(-1, -1), B(0, -1), B(1, -1), B(-1, 1), B(0, 1), B(1, 1), thr) |
-                            detect(B(-1, -1), B(0, -1), B(-1, 0), B(1, 0), B(0, 1), B(1, 1), thr) |
-                            detect(B(-1, 1), B(0, 1), B(-1, 0), B(0, -1), B(1, -1), B(1, 0), thr);
-                    }
-                    e |= (uint32_t)b << k;
-                    v |= 1u << k;
+                    for (int j = 0; j < 3; j++)
+#pragma unroll
+                        for (int k = 0; k < 6; k++) p[j][k] = __ldg(img + (size_t)ys[j] * W + xk[k]);
+                    e = thresholds_exact ? edge_nibble(p, edge_hi) : edge_nibble(p, edge_lut);
+                    v = 0xFu;
+                } else {
+                    edge_gather_ghost(img, W, FH, x4, ym, y, yp, thr, lut, hi_s, thresholds_exact, e, v);
                 }
             }
             if (WRITE_U8) {
