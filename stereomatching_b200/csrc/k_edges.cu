@@ -181,7 +181,9 @@ __global__ void __launch_bounds__(256) k_edge_thresholds(uint32_t *__restrict__ 
 // Padded rows per block and resident blocks per SM of k_edges_planes.  Measured on the fixtures, wrap / ghost
 // (tools/edges_time.py): 8 rows and 56 registers (9 blocks per SM: a 1080p pair is 1.04 waves) 28.4 / 31.8 us at 1080p,
 // 12.3 / 14.4 us at 480x270; 4 rows and 48 registers (10 blocks per SM, one wave) 24.6 / 30.4 and 8.2 / 12.3 us, 4K
-// unchanged (63 / 75 us); 2 rows or fewer lose the sliding window at 4K, 12 blocks per SM spill.
+// unchanged (63 / 75 us); 2 rows or fewer lose the sliding window at 4K, 12 blocks per SM spill.  With the frame's
+// borders on the word path as well (no gather in the regular kernels): 21.6 / 20.4 us at 1080p, 61.5 / 57.4 at 4K,
+// 7.2 / 8.2 at 480x270.
 constexpr int EP_ROWS = 4;
 constexpr int EP_BLOCKS_PER_SM = 10;
 
@@ -207,18 +209,13 @@ struct RowWords {
     uint32_t a, b, c;
 };
 
-// WRAP threads on the word path are interior (4 <= x4 <= W - 8: the seam takes the gather).  GHOST threads may sit at
-// the frame's border: there is nothing beside the frame, and the pixel next to the border is decided without it.
-template <int VARIANT>
-__device__ __forceinline__ RowWords load_row(const uint8_t *__restrict__ row, int x4, int W)
+// The thread's own word and the words left and right of it, at byte columns xl, x4, xr of the row.  Where the words
+// beside come from is decided once per thread: the neighbouring word, or at the frame's border the row's last / first
+// word (WRAP: the torus) or any in-bounds word (GHOST: the pixel next to the border is decided without it).
+__device__ __forceinline__ RowWords load_row(const uint8_t *__restrict__ row, int xl, int x4, int xr)
 {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(row + x4);
-    if (VARIANT == SM_WRAP) return RowWords{__ldg(w - 1), __ldg(w), __ldg(w + 1)};
-    RowWords r;
-    r.b = __ldg(w);
-    r.a = x4 >= 4 ? __ldg(w - 1) : 0u;
-    r.c = x4 + 8 <= W ? __ldg(w + 1) : 0u;
-    return r;
+    return RowWords{__ldg(reinterpret_cast<const uint32_t *>(row + xl)), __ldg(reinterpret_cast<const uint32_t *>(row + x4)),
+                    __ldg(reinterpret_cast<const uint32_t *>(row + xr))};
 }
 
 __device__ __forceinline__ void unpack_row(const RowWords &r, int (&p)[6])
@@ -280,7 +277,10 @@ __device__ __noinline__ void edge_gather_ghost(const uint8_t *__restrict__ img, 
     }
 }
 
-template <int VARIANT, bool WRITE_U8>
+// GENERIC = false: the host has checked that the width is a multiple of 4, the images are word-aligned and the frame
+// has at least two rows, so every thread with pixels is on the word path and the gather (GHOST: with its FP64
+// fallback and the registers it costs around the call) is not even compiled in.
+template <int VARIANT, bool WRITE_U8, bool GENERIC>
 __global__ void __launch_bounds__(128, EP_BLOCKS_PER_SM)
 k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img2, int FH, int row0, PackedGeom g,
                double thr, const uint32_t *__restrict__ lut, uint32_t *__restrict__ LA, uint32_t *__restrict__ LB,
@@ -309,16 +309,18 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
     const int pr0 = blockIdx.y * EP_ROWS, pr1 = min(g.ER, pr0 + EP_ROWS);
     // WRAP: a padding pixel IS the wrapped image pixel, so the thread works at its wrapped column xs (when the
     // width is a multiple of 4 its four pixels stay contiguous there).  Word path (widths that are a multiple of 4,
-    // word-aligned images): WRAP, the four pixels and their neighbours are inside the image (the seam is gathered
-    // through the wrap); GHOST, the four pixels are inside a frame of at least two rows, and a pixel whose stencil
-    // touches the ghost area is an edge without any arithmetic (below).  Everything else is gathered byte by byte.
+    // word-aligned images, frames of at least two rows): the thread's four pixels are inside the image; the words
+    // beside them come through the torus (WRAP) and, GHOST, a pixel whose stencil touches the ghost area is an edge
+    // without any arithmetic (below).  Everything else (GENERIC kernels only) is gathered byte by byte.
     int xs = x4;
     if (VARIANT == SM_WRAP) {
         xs %= W;
         if (xs < 0) xs += W;
     }
-    const bool xfast = wd < g.WPR && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0 &&
-                       (VARIANT == SM_WRAP ? xs >= 4 && xs + 8 <= W : FH >= 2 && xs >= 0 && xs + 4 <= W);
+    const bool xfast = wd < g.WPR && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0 && FH >= 2 && xs >= 0 &&
+                       xs + 4 <= W;
+    const int xl = xs >= 4 ? xs - 4 : (VARIANT == SM_WRAP ? W - 4 : xs);
+    const int xr = xs + 8 <= W ? xs + 4 : (VARIANT == SM_WRAP ? 0 : xs);
     // GHOST: this thread's pixels at the frame's left / right border
     const uint32_t xborder = VARIANT == SM_GHOST ? (xs == 0 ? 1u : 0u) | (xs + 4 == W ? 8u : 0u) : 0u;
     auto frame_row = [&](int pr, bool &valid) {
@@ -369,14 +371,14 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
                 if (ahead_y == yp) {
                     top = ahead;
                 } else {
-                    top = load_row<VARIANT>(img + (size_t)yp * W, xs, W);
+                    top = load_row(img + (size_t)yp * W, xl, xs, xr);
                 }
                 if (have_y == ym) {
 #pragma unroll
                     for (int k = 0; k < 6; k++) p[0][k] = p[1][k], p[1][k] = p[2][k];
                 } else {
-                    unpack_row(load_row<VARIANT>(img + (size_t)ym * W, xs, W), p[0]);
-                    unpack_row(load_row<VARIANT>(img + (size_t)y * W, xs, W), p[1]);
+                    unpack_row(load_row(img + (size_t)ym * W, xl, xs, xr), p[0]);
+                    unpack_row(load_row(img + (size_t)y * W, xl, xs, xr), p[1]);
                 }
                 {
                     // the row below the next step's row (its `yp`), if that step slides on from this one
@@ -384,7 +386,7 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
                     if (VARIANT == SM_WRAP) y2 = y2 >= FH ? y2 - FH : y2;
                     ahead_y = -2;
                     if (pr + 1 < pr1 && nvalid && yn == yp && y2 < FH) {
-                        ahead = load_row<VARIANT>(img + (size_t)y2 * W, xs, W);
+                        ahead = load_row(img + (size_t)y2 * W, xl, xs, xr);
                         ahead_y = y2;
                     }
                 }
@@ -400,8 +402,8 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
                 v = 0xFu;
             } else {
                 have_y = -2;
-                if (VARIANT == SM_WRAP) {
-                    // at the seam of every row (and for widths that are no multiple of 4): every byte through the
+                if (VARIANT == SM_WRAP && GENERIC) {
+                    // widths that are no multiple of 4, unaligned images, one-row frames: every byte through the
                     // wrap, all 18 loads independent (one memory round trip per row, not one per pixel)
                     int xk[6];
 #pragma unroll
@@ -416,9 +418,9 @@ k_edges_planes(const uint8_t *__restrict__ img1, const uint8_t *__restrict__ img
                         for (int k = 0; k < 6; k++) p[j][k] = __ldg(img + (size_t)ys[j] * W + xk[k]);
                     e = thresholds_exact ? edge_nibble(p, edge_hi) : edge_nibble(p, edge_lut);
                     v = 0xFu;
-                } else {
+                } else if (VARIANT == SM_GHOST && GENERIC) {
                     edge_gather_ghost(img, W, FH, x4, ym, y, yp, thr, lut, hi_s, thresholds_exact, e, v);
-                }
+                }  // else: GHOST padding beside the frame, zero and invalid
             }
             if (WRITE_U8) {
                 // the byte maps hold the frame itself: only the unwrapped in-image pixels of this word
@@ -462,13 +464,20 @@ int launch_edges_planes(const uint8_t *img1, const uint8_t *img2, int FH, int ro
     dim3 block(128);
     dim3 grid((g.WPR * 8 + block.x - 1) / block.x, (g.ER + EP_ROWS - 1) / EP_ROWS, 2 * npairs);
     const bool u8 = edges1 != nullptr && edges2 != nullptr;
-#define SM_EP(V, U) \
-    k_edges_planes<V, U><<<grid, block, 0, s>>>(img1, img2, FH, row0, g, threshold, lut, LA, LB, RB, edges1, edges2, \
-                                                image_stride, plane_stride)
-    if (variant == SM_WRAP) {
-        if (u8) SM_EP(SM_WRAP, true); else SM_EP(SM_WRAP, false);
+    // every image of the launch word-aligned, width a multiple of 4, at least two rows: no gather needed (GHOST)
+    const bool regular = (g.W & 3) == 0 && FH >= 2 && ((reinterpret_cast<uintptr_t>(img1) | reinterpret_cast<uintptr_t>(img2)) & 3) == 0 &&
+                         (npairs == 1 || (image_stride & 3) == 0);
+#define SM_EP(V, U, G) \
+    k_edges_planes<V, U, G><<<grid, block, 0, s>>>(img1, img2, FH, row0, g, threshold, lut, LA, LB, RB, edges1, edges2, \
+                                                   image_stride, plane_stride)
+    if (variant == SM_WRAP && regular) {
+        if (u8) SM_EP(SM_WRAP, true, false); else SM_EP(SM_WRAP, false, false);
+    } else if (variant == SM_WRAP) {
+        if (u8) SM_EP(SM_WRAP, true, true); else SM_EP(SM_WRAP, false, true);
+    } else if (regular) {
+        if (u8) SM_EP(SM_GHOST, true, false); else SM_EP(SM_GHOST, false, false);
     } else {
-        if (u8) SM_EP(SM_GHOST, true); else SM_EP(SM_GHOST, false);
+        if (u8) SM_EP(SM_GHOST, true, true); else SM_EP(SM_GHOST, false, true);
     }
 #undef SM_EP
     SM_CUDA(cudaGetLastError());
@@ -494,11 +503,15 @@ void warm_edges(int variant)
     if (variant == SM_WRAP) {
         warm_kernel(k_edges<uint8_t, SM_WRAP>);
         warm_kernel(k_edges<double, SM_WRAP>);
-        warm_kernel(k_edges_planes<SM_WRAP, true>);
-        warm_kernel(k_edges_planes<SM_WRAP, false>);
+        warm_kernel(k_edges_planes<SM_WRAP, true, false>);
+        warm_kernel(k_edges_planes<SM_WRAP, false, false>);
+        warm_kernel(k_edges_planes<SM_WRAP, true, true>);
+        warm_kernel(k_edges_planes<SM_WRAP, false, true>);
     } else {
-        warm_kernel(k_edges_planes<SM_GHOST, true>);
-        warm_kernel(k_edges_planes<SM_GHOST, false>);
+        warm_kernel(k_edges_planes<SM_GHOST, true, false>);
+        warm_kernel(k_edges_planes<SM_GHOST, false, false>);
+        warm_kernel(k_edges_planes<SM_GHOST, true, true>);
+        warm_kernel(k_edges_planes<SM_GHOST, false, true>);
         warm_kernel(k_edges<uint8_t, SM_GHOST>);
         warm_kernel(k_edges<double, SM_GHOST>);
     }
