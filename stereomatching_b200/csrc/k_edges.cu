@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_edge_thresholds(uint32_t *__restrict__ 
 // WRITE_U8: also store the byte maps (in-image pixels only), for sm_download(SM_EDGES*) and the debug planes.
 // Padded rows per block and resident blocks per SM of k_edges_planes.  Measured on the fixtures, wrap / ghost
 // (tools/edges_time.py): 8 rows and 56 registers (9 blocks per SM: a 1080p pair is 1.04 waves) 28.4 / 31.8 us at 1080p,
-// 12.3 / 14.4 us at 480x270; 4 rows and 48 registers (10 blocks per SM, one wave) 24.6 / 30.4 and 8.2 / 12.3 us, 4K
+// 12.3 / 14.4 us at 480x270; 4 rows and 48 registers (10 blocks per SM, shorter serial chains) 24.6 / 30.4 and 8.2 / 12.3 us, 4K
 // unchanged (63 / 75 us); 2 rows or fewer lose the sliding window at 4K, 12 blocks per SM spill.  With the frame's
 // borders on the word path as well (no gather in the regular kernels): 21.6 / 20.4 us at 1080p, 61.5 / 57.4 at 4K,
 // 7.2 / 8.2 at 480x270.
