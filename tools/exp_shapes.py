@@ -36,7 +36,7 @@ POINTS = {
     "small": (240, 135, 30, 21),
 }
 SHAPES = [{}]
-EXTRA = [{"SMB_TR": "16"}, {"SMB_TR": "64"}]
+EXTRA = [{"SMB_TR": "8"}, {"SMB_TR": "16"}, {"SMB_TR": "24"}, {"SMB_TR": "48"}, {"SMB_TR": "64"}, {"SMB_TR": "128"}]
 
 
 def run_point(name, batch=48):
