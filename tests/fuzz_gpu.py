@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """tests/fuzz_gpu.py [n_cases] [seed] -- differential fuzzing of the hot path on the GPU: random geometries (width,
 height, shifts, window, variant, edge density, band), bit-sliced kernel against the direct (literal window sum)
-kernel on the device and, for small frames, against the CPU oracle (checker only).  Exits non-zero on a mismatch."""
+kernel on the device and, for small frames, against the CPU oracle (checker only); every other case starts from
+8-bit images (edge detector straight into the packed planes, random threshold, byte maps against the oracle's).
+Exits non-zero on a mismatch."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,19 +29,39 @@ for case in range(n_cases):
     rows = None
     if h >= 8 and rng.random() < 0.3:
         r0 = int(rng.integers(0, h - 1)); r1 = int(rng.integers(r0 + 1, h + 1)); rows = (r0, r1)
+    # every other case starts from 8-bit IMAGES: the detector writes the packed planes itself (k_edges_planes), at a
+    # random threshold; its byte maps must equal the oracle's and feed the comparison below
+    from_images = bool(rng.random() < 0.5)
+    if from_images:
+        base = rng.integers(0, 256, (h, w)).astype(np.float64)
+        smooth = (base + np.roll(base, 1, 0) + np.roll(base, 1, 1) + np.roll(base, (1, 1), (0, 1))) / 4
+        img1 = np.where(rng.random((h, w)) < dens, base, smooth).astype(np.uint8)
+        img2 = np.roll(img1, int(rng.integers(0, max(1, min(D, w)))), axis=1)
+        img2 = np.where(rng.random((h, w)) < 0.03, rng.integers(0, 256, (h, w)), img2).astype(np.uint8)
+        thr = float(rng.choice([0.0, 0.05, 0.15, 0.3, 1.0]))
+        le, re = orc.edges(img1, thr, variant), orc.edges(img2, thr, variant)
     res = {}
+    edges_ok = True
     for kernel in (smb.KERNEL_BITSLICE, smb.KERNEL_DIRECT):
         with smb.StereoContext(w, h, D, sw, variant, rows=rows, kernel=kernel) as c:
-            c.set_edges(le, re); c.match_wta()
+            if from_images:
+                c.upload_u8(img1, img2); c.edges(thr); c.match_wta()
+                if kernel == smb.KERNEL_BITSLICE:
+                    sle = slice(*rows) if rows else slice(None)
+                    edges_ok = np.array_equal(c.download(smb.EDGES1)[sle], le[sle]) and \
+                               np.array_equal(c.download(smb.EDGES2)[sle], re[sle])
+            else:
+                c.set_edges(le, re); c.match_wta()
             res[kernel] = (c.download(smb.BEST), c.download(smb.WEB))
     sl = slice(*rows) if rows else slice(None)
-    ok = np.array_equal(res[smb.KERNEL_BITSLICE][0][sl], res[smb.KERNEL_DIRECT][0][sl]) and \
+    ok = edges_ok and np.array_equal(res[smb.KERNEL_BITSLICE][0][sl], res[smb.KERNEL_DIRECT][0][sl]) and \
          np.array_equal(res[smb.KERNEL_BITSLICE][1][sl], res[smb.KERNEL_DIRECT][1][sl])
     if ok and w * h * D < 4e6:
         bo, wo = orc.match_wta(le, re, D, sw, variant)
         ok = np.array_equal(res[smb.KERNEL_BITSLICE][0][sl], bo[sl]) and np.array_equal(res[smb.KERNEL_BITSLICE][1][sl], wo[sl])
     if not ok:
         bad += 1
-        print("MISMATCH w=%d h=%d D=%d sw=%d variant=%d dens=%.2f rows=%s" % (w, h, D, sw, variant, dens, rows), flush=True)
+        print("MISMATCH w=%d h=%d D=%d sw=%d variant=%d dens=%.2f rows=%s from_images=%s edges_ok=%s"
+              % (w, h, D, sw, variant, dens, rows, from_images, edges_ok), flush=True)
 print("fuzz: %d cases, %d mismatches" % (n_cases, bad))
 sys.exit(1 if bad else 0)
