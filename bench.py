@@ -700,7 +700,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=256, help="stereo pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs generated per GPU")
-    ap.add_argument("--e2e-pairs", type=int, default=128)
+    ap.add_argument("--e2e-pairs", type=int, default=256, help="pairs per end-to-end step per GPU (the resident step's batch)")
     ap.add_argument("--variant", default="wrap", choices=["wrap", "ghost"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 direct, 2 bit-sliced")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
