@@ -145,27 +145,33 @@ constexpr int LUT_HI = LUT_N * LUT_WORDS, LUT_FLAG = LUT_HI + HI_WORDS;
 
 __global__ void k_edge_thresholds_init(uint32_t *__restrict__ lut) { lut[LUT_FLAG] = 1u; }
 
+// one block per smaller sum m, its threads over the larger one
 __global__ void __launch_bounds__(256) k_edge_thresholds(uint32_t *__restrict__ lut)
 {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= LUT_N) return;
-    int hi = LUT_N - 1;
-    for (int R = m; R < LUT_N; R++)
-        if (lut_bit(lut, m, R)) {
-            hi = R - 1;
-            break;
-        }
-    bool ok = hi >= m - 1;
-    for (int R = 0; R < LUT_N; R++) {
+    const int m = blockIdx.x;
+    __shared__ int first_edge;
+    __shared__ int bad;
+    if (threadIdx.x == 0) first_edge = LUT_N, bad = 0;
+    __syncthreads();
+    for (int R = m + (int)threadIdx.x; R < LUT_N; R += blockDim.x)
+        if (lut_bit(lut, m, R)) atomicMin(&first_edge, R);
+    __syncthreads();
+    const int hi = first_edge - 1;  // the largest R >= m without an edge (LUT_N - 1: none fires)
+    bool ok = true;
+    for (int R = (int)threadIdx.x; R < LUT_N; R += blockDim.x) {
         const int b = lut_bit(lut, m, R);
-        ok = ok && b == lut_bit(lut, R, m);          // symmetric
+        ok = ok && b == lut_bit(lut, R, m);            // symmetric
         if (R >= m) ok = ok && b == (R > hi ? 1 : 0);  // monotone above the diagonal
     }
-    reinterpret_cast<uint16_t *>(lut + LUT_HI)[m] = (uint16_t)(hi < 0 ? 0 : hi);
-    // hi = m - 1 (an edge already at L == R) cannot be told from hi = m at m = 0 once clamped: no such detector
-    // exists (|l - r| = 0 is never above a non-negative limit), and the check keeps it honest
+    // hi = m - 1 would be an edge already at L == R: no such detector exists (|l - r| = 0 is never above a
+    // non-negative limit), and an unsigned table could not hold it at m = 0; the check keeps it honest
     if (hi < m) ok = false;
-    if (!ok) atomicAnd(lut + LUT_FLAG, 0u);
+    if (!ok) bad = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        reinterpret_cast<uint16_t *>(lut + LUT_HI)[m] = (uint16_t)(hi < 0 ? 0 : hi);
+        if (bad) atomicAnd(lut + LUT_FLAG, 0u);
+    }
 }
 
 // ---- edges straight into the packed planes ---------------------------------------------------
@@ -488,7 +494,7 @@ int launch_edge_lut(double threshold, uint32_t *lut, cudaStream_t s)
 {
     k_edge_lut<<<LUT_N, 32, 0, s>>>(threshold, lut);
     k_edge_thresholds_init<<<1, 1, 0, s>>>(lut);
-    k_edge_thresholds<<<(LUT_N + 255) / 256, 256, 0, s>>>(lut);
+    k_edge_thresholds<<<LUT_N, 256, 0, s>>>(lut);
     SM_CUDA(cudaGetLastError());
     return 3;
 }
