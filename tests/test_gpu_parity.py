@@ -382,6 +382,27 @@ def test_run_batch_equals_single_pairs(orc):
             assert np.array_equal(web8[k], wo.astype(np.uint8))
 
 
+@pytest.mark.parametrize("variant", [smb.WRAP, smb.GHOST], ids=vname)
+def test_run_batch_kernel_flavours(orc, variant):
+    """sm_run_batch (images -> planes -> hot path in one pipeline) through every flavour of the hot kernel: half-word
+    pairs with and without column pairs (16 shifts or fewer), column pairs, one word per lane, two words, several
+    64-shift chunks; widths that are a multiple of 4 (regular edge kernels) and not (the gathering ones)."""
+    for (w, h, D, sw) in [(256, 40, 16, 9), (200, 36, 12, 21), (192, 33, 30, 5), (130, 31, 30, 21), (96, 30, 64, 9),
+                          (131, 29, 150, 7), (67, 23, 9, 3)]:
+        n = 5
+        pairs = [orc.synth_pair(4000 + 2 * k, w, h, D) for k in range(n)]
+        first = np.stack([p[0] for p in pairs])
+        second = np.stack([p[1] for p in pairs])
+        with _ctx(w, h, D, sw, variant) as c:
+            web, best = c.run_batch(first, second, THRESHOLD, want_best=True)
+            web8 = c.run_batch(first, second, THRESHOLD, web_u8=True)
+        for k in range(n):
+            e1, e2 = orc.edges(first[k], THRESHOLD, variant), orc.edges(second[k], THRESHOLD, variant)
+            bo, wo = orc.match_wta(e1, e2, D, sw, variant)
+            assert np.array_equal(web[k], wo) and np.array_equal(best[k], bo), (w, h, D, sw, k)
+            assert np.array_equal(web8[k], wo.astype(np.uint8)), (w, h, D, sw, k)
+
+
 def test_batch_kernel_switch_on_one_context(orc):
     """sm_set_kernel between two batch calls with DIFFERENT inputs: the literal kernel must compute every pair
     of the second call (it runs one pair per launch whatever group size the bit-sliced kernel used before)."""
