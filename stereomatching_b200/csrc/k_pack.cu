@@ -37,9 +37,9 @@ k_pack(const uint8_t *__restrict__ e1, const uint8_t *__restrict__ e2, int FH, i
     // latency hides behind this grid's loads.  Measured on config 2, calls back to back: 29.9 us per call
     // with the edge maps in L2 and 30.4 us with cache-cold edge maps.  Triggering at the END of this
     // kernel instead gives 29.4 / 38.4 us (and 48 instead of 52 us on config 4 with warm maps): faster
-    // only as long as every call finds its inputs in L2, so the trigger stays here.  sm_create times
-    // the main kernel's launch shapes under this regime (a dependent under one wave of CTAs is placed
-    // around this grid's still-resident CTAs, which some shapes take badly).
+    // only as long as every call finds its inputs in L2, so the trigger stays here (a dependent under one
+    // wave of CTAs is placed around this grid's still-resident CTAs; the one-pair launch shapes of the
+    // main kernel were calibrated under this regime, tools/sweep_runs.py).
     asm volatile("griddepcontrol.launch_dependents;");
     e1 += blockIdx.z * edge_stride;  // one pair per grid z-slice
     e2 += blockIdx.z * edge_stride;
