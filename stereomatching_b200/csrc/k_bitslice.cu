@@ -44,7 +44,15 @@
 // More than 32*NW shifts are processed as successive chunks over the same rows, merging (best,
 // web) in place (a later chunk holds higher shifts, so it wins ties; the earlier chunks' best of
 // a block's rows is prefetched before pass A).  With 32 shifts or fewer the two words of a lane
-// are two pixels instead (C2, 64-column strips).
+// are two pixels instead (C2, 64-column strips); with 16 or fewer every word serves two pixels, u and
+// u + 16, one per half (HP).
+//
+// A run's first 2*half rows only fill the vertical window: a short block and then whole blocks that add
+// into the sums and the ring and nothing else, in front of the whole, branch-free steady blocks.
+//
+// The ALU pipe binds this kernel (LOP3), so what is not bit-plane logic is kept off it: the selects of the
+// winner-take-all are predicated multiply-adds, store addresses are one widening multiply-add on a per-lane
+// base (FMA pipe), ring slots advance by compare-and-subtract (uniform datapath).
 //
 // Launching.  Several pairs per launch (grid z) run in the throughput shape: runs of about 32
 // windows, several waves deep.  One pair per launch takes the number of row runs a small cost
