@@ -975,7 +975,7 @@ struct Shape {
 
 constexpr int C2_MAX_HALF = 6;
 
-static Shape pick_shape(const HotArgs &h)
+static Shape pick_shape(const HotArgs &h, int num_sms)
 {
     Shape sh;
     sh.seg = 16;
@@ -988,6 +988,14 @@ static Shape pick_shape(const HotArgs &h)
         sh.nw = sh.c2 ? 2 : 1;
         // 16 shifts or fewer: two pixels per word (half-word pairs)
         sh.hp = h.g.D <= 16 && h.g.W >= 64;
+        // One small frame per launch cannot fill the machine with 16-row blocks (480x270 at the reference defaults is
+        // 68 CTAs): 8-pixel walker segments halve the block to 8 rows and double the CTAs.  They cost a quarter more
+        // walker steps per pixel, so batches keep the 16-pixel segments.  Measured, one frame per call: 480x270
+        // 15.5 -> 13.5 us, 327x245 15.4 -> 13.4 us (a call costs the host 13.4 us, which is what 240x135 shows either way).
+        if (sh.nw == 1 && !sh.hp && h.npairs == 1 && num_sms > 0) {
+            const int ctas = ((h.g.W + 31) / 32 + 3) / 4 * ((h.g.BH + 15) / 16);
+            if (ctas < num_sms) sh.seg = 8;
+        }
     }
 #ifdef SMB_DEV  // experiment hooks of the development build only (make DEV=1); never in the shipped library
     if (getenv("SMB_NO_C2") && atoi(getenv("SMB_NO_C2")) && sh.c2) sh.c2 = false, sh.nw = 1;
@@ -1000,7 +1008,17 @@ static Shape pick_shape(const HotArgs &h)
 
 static int dispatch(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
 {
-    const Shape sh = pick_shape(h);
+    if (mode == MODE_PREPARE && h.npairs == 1) {
+        // a context launches one pair at a time AND batches: prepare the batch flavour too if it is another kernel
+        HotArgs hb = h;
+        hb.npairs = 2;
+        const Shape a = pick_shape(h, num_sms), b = pick_shape(hb, num_sms);
+        if (a.seg != b.seg || a.nw != b.nw || a.c2 != b.c2 || a.hp != b.hp) {
+            const int rc = dispatch(hb, num_sms, s, mode);
+            if (rc < 0) return rc;
+        }
+    }
+    const Shape sh = pick_shape(h, num_sms);
     const int half = h.g.half;
 #define SM_SHAPE(HF, NW_, SEG_, C2_, HP_) \
     if (half == HF && sh.nw == NW_ && sh.seg == SEG_ && sh.c2 == C2_ && sh.hp == HP_) \
@@ -1012,6 +1030,7 @@ static int dispatch(const HotArgs &h, int num_sms, cudaStream_t s, int mode)
     SM_HALVES(SM_SHAPE, 1, 16, false, false)
     SM_HALVES(SM_SHAPE, 2, 16, false, false)
     SM_HALVES(SM_SHAPE, 1, 16, false, true)
+    SM_HALVES(SM_SHAPE, 1, 8, false, false)
 #define SM_C2(HP_) \
     SM_SHAPE(0, 2, 16, true, HP_) SM_SHAPE(1, 2, 16, true, HP_) SM_SHAPE(2, 2, 16, true, HP_) SM_SHAPE(3, 2, 16, true, HP_) \
     SM_SHAPE(4, 2, 16, true, HP_) SM_SHAPE(5, 2, 16, true, HP_) SM_SHAPE(6, 2, 16, true, HP_)
@@ -1039,7 +1058,7 @@ int launch_bitslice(const HotArgs &h, int num_sms, cudaStream_t s) { return disp
 int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 {
     // enough pairs that one launch is about three waves of the warps the SMs hold (HotArgs::blocks_per_sm)
-    const int strip_cols = pick_shape(h).strip_cols();
+    const int strip_cols = pick_shape(h, num_sms).strip_cols();
     const int N = 2 * h.g.half + 1, strips = (h.g.W + strip_cols - 1) / strip_cols;
     const int want = throughput_run_windows() * N;
     const int segs = (h.g.BH + want - 1) / want > 0 ? (h.g.BH + want - 1) / want : 1;
@@ -1053,6 +1072,6 @@ int bitslice_pairs_per_launch(const HotArgs &h, int num_sms, int max_pairs)
 // sm_match_wta call pays none of that; returns its resident warps per SM (for HotArgs::blocks_per_sm).
 int prepare_bitslice(const HotArgs &h, int num_sms) { return dispatch(h, num_sms, nullptr, MODE_PREPARE); }
 
-int bitslice_tmem_columns(const HotArgs &h) { return dispatch(h, 0, nullptr, MODE_TMEM_COLUMNS); }
+int bitslice_tmem_columns(const HotArgs &h) { return dispatch(h, 0, nullptr, MODE_TMEM_COLUMNS); }  // (of the 16-pixel-segment flavour)
 
 }  // namespace smb
